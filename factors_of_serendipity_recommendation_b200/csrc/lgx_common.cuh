@@ -1,0 +1,75 @@
+// Shared helpers for liblgx: error slot, CUDA checks, the graph handle layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/lgx.h"
+
+namespace lgx {
+
+void set_error(const std::string& msg);
+int device_ok();   // LGX_OK iff current device is sm_100; sets the error otherwise
+int sm_count();
+
+#define LGX_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::lgx::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + \
+                       __FILE__ + ":" + std::to_string(__LINE__) + ")");                  \
+      return LGX_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define LGX_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      ::lgx::set_error(std::string("invalid argument: ") + msg); \
+      return LGX_ERR_INVALID;                                   \
+    }                                                           \
+  } while (0)
+
+#define LGX_CHECK_DEVICE()               \
+  do {                                   \
+    int _d = ::lgx::device_ok();         \
+    if (_d != LGX_OK) return _d;         \
+  } while (0)
+
+#define LGX_CHECK_LAUNCH() LGX_CHECK_CUDA(cudaGetLastError())
+
+// One schedulable unit of SpMM work: a run of <= chunk_nnz non-zeros of one row.
+// Rows longer than chunk_nnz come first in the degree-descending schedule, so the units of split
+// rows are exactly units [0, n_partials) and a split unit's partial slot is its own index.
+struct WorkItem {
+  int64_t start;    // offset into indices / values
+  int32_t row;      // output row
+  int32_t len;      // number of non-zeros in this unit
+};
+static_assert(sizeof(WorkItem) == 16, "WorkItem is read as one int4");
+
+// A row that was split into several units; reduced in fixed order by the long-row kernel.
+struct LongRow {
+  int32_t row;
+  int32_t first_partial;
+  int32_t n_partials;
+  int32_t pad;
+};
+
+}  // namespace lgx
+
+struct lgx_graph {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int32_t n_users = 0, m_items = 0;
+  int32_t chunk_nnz = 0;
+  int64_t n_work = 0, n_long = 0, n_partials = 0, max_row_nnz = 0;
+  int64_t* indptr = nullptr;     // [n_rows + 1]
+  int32_t* indices = nullptr;    // [nnz]
+  float* values = nullptr;       // [nnz]
+  int32_t* degree = nullptr;     // [n_rows] sum of multiplicities (0 for from_csr graphs: stored nnz)
+  float* dinv = nullptr;         // [n_rows]
+  int32_t* row_order = nullptr;  // [n_rows] stable degree-descending
+  lgx::WorkItem* work = nullptr; // [n_work]
+  lgx::LongRow* long_rows = nullptr;  // [n_long]
+};

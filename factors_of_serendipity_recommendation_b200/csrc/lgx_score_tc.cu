@@ -1,0 +1,443 @@
+// Fused full-catalogue scoring + train mask + top-K on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces getUsersRating (PT/model.py:179-184: SGEMM [B,d]x[d,M] + sigmoid), the train-item mask
+// (PT/Procedure.py:129-134), torch.topk (:135) and the dead 36 MB/batch score-matrix D2H (:136).
+// The [B, M] score matrix lives only in TMEM: it never reaches shared memory, L2 or HBM.
+//
+// One CTA = 128 users (UMMA M, one TMEM lane per user) x one split of the item catalogue.
+//   warp 0      TMA producer: user tile once (resident in smem), then item K-blocks [256 x 64] bf16
+//               through an mbarrier ring (cp.async.bulk.tensor, SWIZZLE_128B)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::f16 (M128 N256 K16), fp32
+//               accumulators double-buffered in TMEM (2 x 256 columns), tcgen05.commit -> mbarriers
+//   warp 2      TMEM allocator / deallocator
+//   warps 4-11  epilogue: each thread owns one user row (TMEM lane) and one 128-column half of the
+//               tile: tcgen05.ld 32 columns at a time, max-filter against the row's running K-th
+//               score, rare slow path = train-mask binary search + sorted insert into the thread's
+//               private top-K list (shared memory, column layout).
+// bf16x3 mode runs the same kernel with K = 3d over split operands (hi.hi + hi.lo + lo.hi).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "lgx_common.cuh"
+#include "lgx_score_plan.cuh"
+#include "lgx_topk.cuh"
+
+namespace lgx {
+
+int launch_merge_i32(const float* ws_val, const int32_t* ws_idx, int P, int B, int K, int64_t item_offset,
+                     int64_t m_local, TrainMask mask, const int64_t* users, int64_t* out_idx, float* out_val,
+                     cudaStream_t st);
+TrainMask make_mask(const lgx_graph* g);
+int score_topk_fp32(const lgx_graph* g, const float* U, const int64_t* users, int B, const float* I, int M, int d,
+                    int K, int64_t item_offset, int64_t* out_idx, float* out_val, void* workspace, cudaStream_t st);
+
+constexpr int TC_TILE_U = 128;                 // UMMA M
+constexpr int TC_TILE_I = 256;                 // UMMA N
+constexpr int TC_KBLK = 64;                    // bf16 elements per K-block = one 128-byte swizzle row
+constexpr int TC_A_BLOCK_BYTES = TC_TILE_U * TC_KBLK * 2;   // 16 KB
+constexpr int TC_B_STAGE_BYTES = TC_TILE_I * TC_KBLK * 2;   // 32 KB
+constexpr int TC_THREADS = 384;
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_SMEM_LIMIT = 232448;          // 227 KB opt-in limit per CTA
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)(1024u >> 4) << 32;           // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128.
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE_I >> 3) << 17) |
+                                ((uint32_t)(TC_TILE_U >> 4) << 24);
+
+#define LGX_TMEM_LD32(v, taddr)                                                                          \
+  asm volatile(                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                          \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"          \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),         \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),       \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),       \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                            \
+      : "r"(taddr)                                                                                       \
+      : "memory")
+// The wait names the destination registers as in/out operands so the compiler cannot hoist their
+// uses above it (the values are only defined once the wait retires).
+#define LGX_TMEM_WAIT(v)                                                                                  \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                           \
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),      \
+                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),  \
+                 "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]),            \
+                 "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]),            \
+                 "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])             \
+               :                                                                                          \
+               : "memory")
+
+struct TcParams {
+  int B, M, K;            // users in batch, local items, top-K
+  int k_blocks, stages;   // 64-wide K blocks per tile, B-operand ring depth
+  int n_splits, tiles_per_split;
+  int64_t item_offset;
+  TrainMask mask;
+  const int64_t* users;   // global user id per batch row (mask lookup) or NULL
+  float* ws_val;          // [n_splits, B, K]
+  int32_t* ws_idx;
+};
+
+// Check one 32-column chunk against the row threshold; insert survivors.
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int j0, float& thresh, const TcParams& p,
+                                          int64_t uid, float* lval, int32_t* lidx) {
+  float m = __uint_as_float(v[0]);
+#pragma unroll
+  for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+  if (m > thresh) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float s = __uint_as_float(v[i]);
+      if (s > thresh) {
+        const int j = j0 + i;
+        if (j < p.M && !p.mask.contains(uid, p.item_offset + j))
+          thresh = topk_insert(lval, lidx, p.K, TC_EPI_THREADS, s, j);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_i,
+                const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* gbase = smem_dyn + (base - raw);
+  const uint32_t sA = base;
+  const uint32_t sB = sA + (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES;
+  const uint32_t off_lists = (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES + (uint32_t)p.stages * TC_B_STAGE_BYTES;
+  float* lval_all = reinterpret_cast<float*>(gbase + off_lists);
+  int32_t* lidx_all = reinterpret_cast<int32_t*>(gbase + off_lists + (size_t)p.K * TC_EPI_THREADS * 4);
+  const uint32_t off_bar = off_lists + (uint32_t)p.K * TC_EPI_THREADS * 8;
+  const uint32_t bar_full = base + off_bar;                     // [stages]
+  const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [stages]
+  const uint32_t bar_a = bar_empty + 8 * TC_MAX_STAGES;
+  const uint32_t bar_tfull = bar_a + 8;                         // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u_tile = blockIdx.x, split = blockIdx.y;
+  const int n_tiles = (p.M + TC_TILE_I - 1) / TC_TILE_I;
+  const int t_begin = split * p.tiles_per_split;
+  const int n_my = max(0, min(n_tiles, t_begin + p.tiles_per_split) - t_begin);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_u)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_i)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, TC_EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 4) {
+    const int col = threadIdx.x - 128;
+    for (int k = 0; k < p.K; ++k) {
+      lval_all[k * TC_EPI_THREADS + col] = -CUDART_INF_F;
+      lidx_all[k * TC_EPI_THREADS + col] = INT32_MAX;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_my > 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_expect_tx(bar_a, (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES);
+      for (int kb = 0; kb < p.k_blocks; ++kb)
+        tma_load_2d(sA + kb * TC_A_BLOCK_BYTES, &tmap_u, bar_a, kb * TC_KBLK, u_tile * TC_TILE_U);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int row0 = (t_begin + it) * TC_TILE_I;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, TC_B_STAGE_BYTES);
+          tma_load_2d(sB + stage * TC_B_STAGE_BYTES, &tmap_i, bar_full + 8 * stage, kb * TC_KBLK, row0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_my > 0) {
+      // ---------------------------------------------------------------- MMA issuer (one thread)
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_TILE_I;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(sA + kb * TC_A_BLOCK_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(sB + stage * TC_B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_KBLK / 16; ++k)   // advance 16 bf16 = 32 B inside the swizzle atom: +2 in 16-byte units
+            tc_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescBf16,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * stage);          // frees the smem stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * buf);              // accumulator tile complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (256 threads)
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int h = (warp - 4) >> 2;            // which 128-column half of the tile
+    const int row = q * 32 + lane;            // user row inside the tile == TMEM lane
+    const int col = h * TC_TILE_U + row;      // this thread's list column
+    float* lval = lval_all + col;
+    int32_t* lidx = lidx_all + col;
+    const int u = u_tile * TC_TILE_U + row;
+    const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
+    float thresh = -CUDART_INF_F;
+    for (int it = 0; it < n_my; ++it) {
+      const int buf = it & 1;
+      mbar_wait(bar_tfull + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_TILE_I + h * 128);
+      const int j_base = (t_begin + it) * TC_TILE_I + h * 128;
+      uint32_t va[32], vb[32];
+      LGX_TMEM_LD32(va, taddr);
+      LGX_TMEM_WAIT(va);
+      LGX_TMEM_LD32(vb, taddr + 32);
+      epi_chunk(va, j_base, thresh, p, uid, lval, lidx);
+      LGX_TMEM_WAIT(vb);
+      LGX_TMEM_LD32(va, taddr + 64);
+      epi_chunk(vb, j_base + 32, thresh, p, uid, lval, lidx);
+      LGX_TMEM_WAIT(va);
+      LGX_TMEM_LD32(vb, taddr + 96);
+      epi_chunk(va, j_base + 64, thresh, p, uid, lval, lidx);
+      LGX_TMEM_WAIT(vb);
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);      // TMEM buffer may be overwritten
+      epi_chunk(vb, j_base + 96, thresh, p, uid, lval, lidx);
+    }
+    // merge the two column halves of every row and publish the split's partial list
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (h == 0 && u < p.B) {
+      const float* v0 = lval_all + row;  const int32_t* i0 = lidx_all + row;
+      const float* v1 = lval_all + TC_TILE_U + row;  const int32_t* i1 = lidx_all + TC_TILE_U + row;
+      int a = 0, b = 0;
+      const int64_t o = ((int64_t)split * p.B + u) * p.K;
+      for (int k = 0; k < p.K; ++k) {
+        const float fa = v0[a * TC_EPI_THREADS], fb = v1[b * TC_EPI_THREADS];
+        const int32_t ia = i0[a * TC_EPI_THREADS], ib = i1[b * TC_EPI_THREADS];
+        if (better(fa, ia, fb, ib) || (fa == fb && ia == ib)) { p.ws_val[o + k] = fa; p.ws_idx[o + k] = ia; ++a; }
+        else { p.ws_val[o + k] = fb; p.ws_idx[o + k] = ib; ++b; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// [rows, ktot] bf16 row-major -> boxes of [box_rows x 64] with the 128-byte swizzle
+static int make_operand_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LGX_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KBLK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return LGX_ERR_CUDA; }
+  return LGX_OK;
+}
+
+struct TcConfig { int k_blocks, stages; size_t smem; bool ok; };
+
+static TcConfig tc_config(int d, int K, int mode) {
+  TcConfig c{};
+  const int ktot = mode == LGX_SCORE_BF16X3 ? 3 * d : d;
+  c.ok = (d % TC_KBLK == 0) && K >= 1 && K <= 64;
+  c.k_blocks = ktot / TC_KBLK;
+  const size_t fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)K * TC_EPI_THREADS * 8 +
+                       8 * (2 * TC_MAX_STAGES + 5) + 16;
+  if (!c.ok || fixed + 2 * (size_t)TC_B_STAGE_BYTES > TC_SMEM_LIMIT) { c.ok = false; return c; }
+  c.stages = (int)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / TC_B_STAGE_BYTES);
+  c.smem = fixed + (size_t)c.stages * TC_B_STAGE_BYTES;
+  return c;
+}
+
+static ScorePlan tc_plan(int B, int M) { return plan_score(B, M, TC_TILE_U, TC_TILE_I, sm_count(), 1); }
+
+static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* users, int B, const void* I_op, int M,
+                         int d, int K, int mode, int64_t item_offset, int64_t* out_idx, float* out_val,
+                         void* workspace, cudaStream_t st) {
+  const TcConfig cfg = tc_config(d, K, mode);
+  if (!cfg.ok) {
+    set_error("tcgen05 scoring needs d % 64 == 0, k <= 64 and the user tile + 2 item stages to fit in 227 KB "
+              "(d<=256 for bf16, d<=128 for bf16x3); use LGX_SCORE_FP32 otherwise");
+    return LGX_ERR_INVALID;
+  }
+  const int ktot = cfg.k_blocks * TC_KBLK;
+  CUtensorMap tm_u, tm_i;
+  int rc = make_operand_map(&tm_u, U_op, B, ktot, TC_TILE_U);
+  if (rc != LGX_OK) return rc;
+  rc = make_operand_map(&tm_i, I_op, M, ktot, TC_TILE_I);
+  if (rc != LGX_OK) return rc;
+  const ScorePlan plan = tc_plan(B, M);
+  TcParams p;
+  p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages;
+  p.n_splits = plan.n_splits; p.tiles_per_split = plan.tiles_per_split; p.item_offset = item_offset;
+  p.mask = make_mask(g); p.users = users;
+  p.ws_val = reinterpret_cast<float*>(workspace);
+  p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
+  static size_t configured = 0;
+  if (cfg.smem > configured) {
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    configured = cfg.smem;
+  }
+  dim3 grid(plan.n_user_tiles, plan.n_splits);
+  k_score_topk_tc<<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  LGX_CHECK_LAUNCH();
+  return launch_merge_i32(p.ws_val, p.ws_idx, plan.n_splits, B, K, item_offset, M, p.mask, users, out_idx, out_val, st);
+}
+
+}  // namespace lgx
+
+using namespace lgx;
+
+extern "C" {
+
+size_t lgx_score_topk_workspace_bytes(int32_t B, int32_t M, int32_t d, int32_t k, int32_t mode) {
+  if (B <= 0 || M <= 0 || k <= 0) return 0;
+  (void)d;
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) sms = sm_count(); else cudaGetLastError();
+  const ScorePlan plan = mode == LGX_SCORE_FP32 ? plan_score(B, M, 64, 64, sms, 4)
+                                                : plan_score(B, M, TC_TILE_U, TC_TILE_I, sms, 1);
+  return (size_t)plan.n_splits * B * k * 8 + 256;
+}
+
+int lgx_score_topk(const lgx_graph* g, const void* U_op, const int64_t* users, int32_t B, const void* I_op, int32_t M,
+                   int32_t d, int32_t k, int32_t mode, int64_t item_offset, int64_t* out_idx, float* out_val,
+                   void* workspace, size_t workspace_bytes, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(U_op && I_op && out_idx && out_val && workspace, "NULL argument");
+  LGX_REQUIRE(B > 0 && M > 0 && d > 0, "B, M, d must be positive");
+  LGX_REQUIRE(k > 0 && k <= M && k <= 255, "k must be in [1, min(M, 255)]");
+  LGX_REQUIRE(g == nullptr || users != nullptr || B <= g->n_users, "mask needs user ids");
+  LGX_REQUIRE(mode == LGX_SCORE_FP32 || mode == LGX_SCORE_BF16 || mode == LGX_SCORE_BF16X3, "unknown mode");
+  if (workspace_bytes < lgx_score_topk_workspace_bytes(B, M, d, k, mode)) {
+    set_error("workspace too small for lgx_score_topk");
+    return LGX_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == LGX_SCORE_FP32)
+    return score_topk_fp32(g, reinterpret_cast<const float*>(U_op), users, B, reinterpret_cast<const float*>(I_op), M,
+                           d, k, item_offset, out_idx, out_val, workspace, st);
+  LGX_REQUIRE((reinterpret_cast<uintptr_t>(U_op) & 15) == 0 && (reinterpret_cast<uintptr_t>(I_op) & 15) == 0,
+              "packed operands must be 16-byte aligned");
+  return score_topk_tc(g, U_op, users, B, I_op, M, d, k, mode, item_offset, out_idx, out_val, workspace, st);
+}
+
+}  // extern "C"

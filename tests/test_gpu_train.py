@@ -1,0 +1,132 @@
+"""BPR loss / backward / Adam / sampler / metrics kernels vs the reference's golden training step (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lightgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def make(mlls, t, **cfg_over):
+    from factors_of_serendipity_recommendation_b200 import dataloader, model, world
+    cfg = dict(world.config)
+    cfg.update(lightGCN_n_layers=int(t["n_layers"]), pretrain=1, user_emb=t["w0_user"], item_emb=t["w0_item"],
+               lr=float(t["lr"]), decay=float(t["decay"]))
+    cfg.update(cfg_over)
+    ds = dataloader.InteractionDataset(mlls["n_users"], mlls["m_items"], mlls["train_user"], mlls["train_item"],
+                                       test_dict=mlls["test_dict"], device="cuda")
+    return model.LightGCN(cfg, ds).cuda().train(), ds, cfg
+
+
+def batch(t):
+    return tuple(torch.from_numpy(t[k]).long().cuda() for k in ("users", "pos", "neg"))
+
+
+def test_bpr_loss_and_gradients_match_reference(mlls, train_step):
+    t = train_step
+    m, _, cfg = make(mlls, t)
+    u, p, n = batch(t)
+    loss, reg = m.bpr_loss(u, p, n)
+    assert loss.dim() == 0 and reg.dim() == 0 and loss.requires_grad
+    assert abs(loss.item() - float(t["loss"])) <= 1e-5 * abs(float(t["loss"]))
+    assert abs(reg.item() - float(t["reg_loss"])) <= 1e-5 * abs(float(t["reg_loss"]))
+    (loss + reg * cfg["decay"]).backward()
+    assert rel_err(m.embedding_user.weight.grad.cpu().numpy(), t["grad_user"]) <= 1e-5
+    assert rel_err(m.embedding_item.weight.grad.cpu().numpy(), t["grad_item"]) <= 1e-5
+
+
+def test_reference_style_loss_on_top_of_computer(mlls, train_step):
+    """The reference's own bpr_loss body (gathers + softplus in torch) on our computer(): autograd glue."""
+    t = train_step
+    m, _, cfg = make(mlls, t)
+    u, p, n = batch(t)
+    ue, pe, ne, u0, p0, n0 = m.getEmbedding(u, p, n)
+    reg = 0.5 * (u0.norm(2).pow(2) + p0.norm(2).pow(2) + n0.norm(2).pow(2)) / float(len(u))
+    loss = torch.mean(torch.nn.functional.softplus((ue * ne).sum(1) - (ue * pe).sum(1)))
+    assert abs(loss.item() - float(t["loss"])) <= 1e-5
+    (loss + reg * cfg["decay"]).backward()
+    assert rel_err(m.embedding_user.weight.grad.cpu().numpy(), t["grad_user"]) <= 1e-5
+    assert rel_err(m.embedding_item.weight.grad.cpu().numpy(), t["grad_item"]) <= 1e-5
+    gamma = m.forward(u[:64], p[:64])
+    assert gamma.shape == (64,)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_stage_one_step_matches_reference(mlls, train_step, fused):
+    from factors_of_serendipity_recommendation_b200 import utils
+    t = train_step
+    m, _, cfg = make(mlls, t, fused_adam=fused)
+    bpr = utils.BPRLoss(m, cfg)
+    u, p, n = batch(t)
+    cri = bpr.stageOne(u, p, n)
+    assert isinstance(cri, float)
+    assert abs(cri - (float(t["loss"]) + float(t["decay"]) * float(t["reg_loss"]))) <= 1e-5
+    # Adam's first step moves every touched weight by ~lr: compare the update itself
+    du = m.embedding_user.weight.detach().cpu().numpy() - t["w0_user"]
+    di = m.embedding_item.weight.detach().cpu().numpy() - t["w0_item"]
+    ru, ri = t["w1_user"] - t["w0_user"], t["w1_item"] - t["w0_item"]
+    assert np.abs(du - ru).max() <= 2e-5 * float(t["lr"]) + 1e-7 * 0 + 5e-8
+    assert np.abs(di - ri).max() <= 2e-5 * float(t["lr"]) + 5e-8
+    m.eval()
+    with torch.no_grad():
+        gamma = m.forward(u[:64], p[:64])
+    assert np.abs(gamma.cpu().numpy() - t["gamma_after"]).max() <= 1e-5 * np.abs(t["gamma_after"]).max() + 1e-7
+    # a second step runs and the eval cache saw the update
+    c2 = bpr.stageOne(u, p, n, sync=False)
+    assert torch.is_tensor(c2) and c2.item() < cri
+
+
+def test_adam_kernel_matches_torch():
+    from factors_of_serendipity_recommendation_b200 import _lgx
+    torch.manual_seed(0)
+    p = torch.randn(1000, 64, device="cuda")
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn_like(p)
+        ref.grad = g.clone()
+        opt.step()
+        _lgx.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+        assert (p - ref.detach()).abs().max().item() <= 1e-6
+
+
+def test_device_sampler(mlls):
+    from factors_of_serendipity_recommendation_b200 import dataloader, utils
+    ds = dataloader.InteractionDataset(mlls["n_users"], mlls["m_items"], mlls["train_user"], mlls["train_item"], device="cuda")
+    S = utils.UniformSample_original(ds, seed=7)
+    assert S.shape == (ds.trainDataSize, 3) and S.dtype == torch.int64
+    S2 = utils.UniformSample_original(ds, seed=7)
+    assert torch.equal(S, S2)                                       # counter-based: reproducible
+    S = S.cpu().numpy()
+    train = set((mlls["train_user"].astype(np.int64) * ds.m_items + mlls["train_item"]).tolist())
+    assert all(int(u) * ds.m_items + int(p) in train for u, p, _ in S[:5000])
+    assert not any(int(u) * ds.m_items + int(n) in train for u, _, n in S[:5000])
+    assert S[:, 2].min() >= 0 and S[:, 2].max() < ds.m_items
+    # user marginal is uniform (PT/utils.py:76): chi-square-ish bound
+    cnt = np.bincount(S[:, 0], minlength=ds.n_users)
+    assert abs(cnt.mean() - ds.trainDataSize / ds.n_users) < 1e-9 and cnt.std() < 3 * np.sqrt(cnt.mean())
+    # sampling.cpp semantics: every user exactly per_user triples (PT/sources/sampling.cpp:29-42)
+    P = ds.getGraphHandle().sample_bpr(0, per_user=3, seed=1).cpu().numpy()
+    assert P.shape == (ds.n_users * 3, 3) and np.array_equal(P[:, 0], np.repeat(np.arange(ds.n_users), 3))
+
+
+def test_train_epoch_runs_and_learns(mlls, train_step):
+    from factors_of_serendipity_recommendation_b200 import Procedure, utils, world
+    t = train_step
+    m, ds, cfg = make(mlls, t, lr=0.01)
+    world.configure(bpr_batch_size=2048, topks=[20])
+    bpr = utils.BPRLoss(m, cfg)
+    np.random.seed(0)
+    before = Procedure.Test(ds, m, 0)["recall"][0]
+    for ep in range(3):
+        info = Procedure.BPR_train_original(ds, m, bpr, ep)
+    assert info.startswith("loss") and "Sample" in info
+    after = Procedure.Test(ds, m, 3)["recall"][0]
+    assert after > before + 0.02                                    # random init ~0.01 -> learns
