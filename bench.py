@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- LightGCN forward (3-layer propagation) + full-catalogue top-20 scoring.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over the whole synthetic graph of the named shape:
+computer() (L fused SpMM layers) followed by fused score + train-mask + top-20 for EVERY user.
+Prints ONE JSON line (see the round prompt for the contract).  metric = users scored top-20 / s
+over the whole step (propagation included); the SpMM propagated-edges/s + HBM GB/s and the scoring
+TFLOP/s are in the `spmm` / `scoring` / `roofline*` objects of the same line.
+
+--impl reference times the reference's CPU code path (oracle port: the same torch.sparse.mm /
+matmul / topk calls, PT/Procedure.py:121-135 as written) on the host cores, one 100-user Test batch
+per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+K_TOP = 20
+N_LAYERS = 3
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sustained=j.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def spmm_algorithmic_bytes(n_nodes, nnz, d, n_layers):
+    """per layer nnz*(4+4) + (N+1)*4 + 2*N*d*4; forward adds one write of the mean."""
+    layer = nnz * 8 + (n_nodes + 1) * 4 + 2 * n_nodes * d * 4
+    return layer, n_layers * layer + n_nodes * d * 4
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args, shape):
+    import torch
+    from factors_of_serendipity_recommendation_b200 import synth
+    from oracle import lightgcn_oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nu, mi, E, d = shape
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    u, i = synth.make_interactions(nu, mi, E, seed=2020)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=2020)
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=N_LAYERS, user_emb=ue, item_emb=ie)
+    batch = 100                                             # --testbatch default, PT/parse.py:26
+    rng = np.random.default_rng(0)
+    times = []
+    with torch.no_grad():
+        for s in range(args.warmup + args.steps):
+            users = rng.choice(nu, size=batch, replace=False)
+            t0 = time.perf_counter()
+            rating = ref.getUsersRating(torch.from_numpy(users))          # recomputes computer(), PT/model.py:180
+            O.mask_and_topk(rating, ref.all_pos(users), K_TOP)            # PT/Procedure.py:129-135
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = batch * len(times) / total
+    line = {
+        "impl": "reference", "metric": "users scored top-20/sec (3-layer propagation + full-catalogue scoring)",
+        "value": value, "unit": "users/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "n_users": nu, "m_items": mi, "edges": E, "d": d, "layers": N_LAYERS, "k": K_TOP},
+        "cpu_baseline": {"value": value, "unit": "users/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} Test batches of {batch} users as written in PT/Procedure.py:121-135 "
+                                   "(getUsersRating recomputes computer() per batch), torch CPU ops, all host threads"},
+        "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(shape, u, i, ue, ie, budget_s=20.0):
+    """Oracle port on the host cores, bounded: one computer() + as many 100-user batches as fit ~budget."""
+    import torch
+    from oracle import lightgcn_oracle as O
+
+    nu, mi, E, d = shape
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=N_LAYERS, user_emb=ue, item_emb=ie)
+    rng = np.random.default_rng(0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        au, ai = ref.computer()
+        t_prop = time.perf_counter() - t0
+        n_b, t_batches, t_score_only = 0, 0.0, 0.0
+        while n_b < 2 or (t_batches < budget_s and n_b < 12):
+            users = rng.choice(nu, size=100, replace=False)
+            t0 = time.perf_counter()
+            rating = ref.getUsersRating(torch.from_numpy(users))
+            O.mask_and_topk(rating, ref.all_pos(users), K_TOP)
+            t_batches += time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rating = O.users_rating(au, ai, torch.from_numpy(users))
+            O.mask_and_topk(rating, ref.all_pos(users), K_TOP)
+            t_score_only += time.perf_counter() - t0
+            n_b += 1
+    as_written = 100 * n_b / t_batches
+    hoisted = nu / (t_prop + (nu / 100.0) * (t_score_only / n_b))
+    return {"value": as_written, "unit": "users/s", "cores": cores, "kind": "port",
+            "sample": f"{n_b} Test batches of 100 users as written (PT/Procedure.py:121-135: computer() recomputed per "
+                      f"batch); computer() alone {t_prop * 1e3:.0f} ms = {N_LAYERS * 2 * E / t_prop / 1e6:.1f} M edges/s; "
+                      f"with computer() hoisted out of the loop the same code would give {hoisted:.0f} users/s",
+            "propagate_ms": t_prop * 1e3, "edges_per_s": N_LAYERS * 2 * E / t_prop, "hoisted_users_per_s": hoisted}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, shape):
+    import torch
+    import torch.distributed as dist
+    from factors_of_serendipity_recommendation_b200 import _lgx, dataloader, model, synth, world
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size != args.gpus and world_size > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world_size}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    nu, mi, E, d = shape
+    mode = args.mode
+    mode_id = _lgx.MODES[mode]
+
+    u, i = synth.make_interactions(nu, mi, E, seed=2020)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=2020)
+    cfg = dict(world.config)
+    cfg.update(pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy(), lightGCN_n_layers=N_LAYERS, latent_dim_rec=d,
+               score_mode=mode)
+    ds = dataloader.InteractionDataset(nu, mi, u, i, device=dev)
+    m = model.LightGCN(cfg, ds).to(dev).eval()
+    g = ds.getGraphHandle()
+    N, nnz = g.n_rows, g.nnz
+    all_users = torch.arange(nu, dtype=torch.int64, device=dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    if world_size > 1:
+        from factors_of_serendipity_recommendation_b200 import parallel
+        engine = parallel.ShardedEngine(g, nu, mi, d, N_LAYERS, rank, world_size, dev)
+    else:
+        engine = None
+
+    E0 = m._flat_if_fused()
+    assert E0 is not None
+    light = torch.empty_like(E0)
+
+    def step_resident():
+        """inputs resident in HBM; returns event triplet timings handled by the caller"""
+        if engine is not None:
+            return engine.step(E0, all_users, K_TOP, mode_id)
+        g.propagate_fwd(E0, N_LAYERS, out=light)
+        au, ai = light[:nu], light[nu:]
+        if mode_id == _lgx.SCORE_FP32:
+            U_op, I_op = au, ai
+        else:
+            I_op = _lgx.pack_operand(ai, None, mode_id, True)
+            U_op = _lgx.pack_operand(au, None, mode_id, False)
+        return _lgx.score_topk(g, U_op, all_users, I_op, d, K_TOP, mode_id)
+
+    def timed_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        flush.fill_(1)                                        # evict L2 between timed iterations
+        if engine is not None:
+            ev[0].record()
+            engine.step(E0, all_users, K_TOP, mode_id, events=ev)
+            ev[3].record()
+            return ev
+        ev[0].record()
+        g.propagate_fwd(E0, N_LAYERS, out=light)
+        ev[1].record()
+        au, ai = light[:nu], light[nu:]
+        if mode_id == _lgx.SCORE_FP32:
+            U_op, I_op = au, ai
+        else:
+            I_op = _lgx.pack_operand(ai, None, mode_id, True)
+            U_op = _lgx.pack_operand(au, None, mode_id, False)
+        ev[2].record()
+        _lgx.score_topk(g, U_op, all_users, I_op, d, K_TOP, mode_id)
+        ev[3].record()
+        return ev
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        timed_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [timed_step() for _ in range(args.steps)]
+    barrier()
+    t_step = [e[0].elapsed_time(e[3]) for e in evs]
+    t_prop = [e[0].elapsed_time(e[1]) for e in evs]
+    t_pack = [e[1].elapsed_time(e[2]) for e in evs]
+    t_score = [e[2].elapsed_time(e[3]) for e in evs]
+    total_ms = sum(t_step)
+    if world_size > 1:
+        tt = torch.tensor([total_ms, sum(t_prop), sum(t_pack), sum(t_score)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)             # max over ranks, device-timed
+        total_ms, sp, spk, ss = tt.tolist()
+        t_prop_mean, t_pack_mean, t_score_mean = sp / args.steps, spk / args.steps, ss / args.steps
+    else:
+        t_prop_mean, t_pack_mean, t_score_mean = (statistics.mean(x) for x in (t_prop, t_pack, t_score))
+    ms_per_step = total_ms / args.steps
+    value = nu / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (H2D of the tables, D2H of the top-20)
+    host_u, host_i = ue.clone().pin_memory(), ie.clone().pin_memory()
+    host_out = torch.empty(nu, K_TOP, dtype=torch.int64).pin_memory()
+    e2e_ms = []
+
+    def e2e_step():
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        m.embedding_user.weight.data.copy_(host_u, non_blocking=True)
+        m.embedding_item.weight.data.copy_(host_i, non_blocking=True)
+        m._eval_cache = None
+        if engine is not None:
+            idx, _ = engine.step(m._flat_if_fused(), all_users, K_TOP, mode_id)
+        else:
+            idx, _ = m.topk(all_users, K_TOP, mode=mode)      # the call a user makes (computer() inside)
+        host_out.copy_(idx, non_blocking=True)
+        b.record()
+        return a, b
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    pairs = [e2e_step() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_total = sum(a.elapsed_time(b) for a, b in pairs)
+    if world_size > 1:
+        tt = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_total = tt.item()
+    e2e_value = nu / (e2e_total / args.steps * 1e-3)
+
+    if rank == 0:
+        layer_bytes, fwd_bytes = spmm_algorithmic_bytes(N, nnz, d, N_LAYERS)
+        spmm_gbs = fwd_bytes / (t_prop_mean * 1e-3) / 1e9
+        flops = 2.0 * nu * mi * d
+        score_tf = flops / (t_score_mean * 1e-3) / 1e12
+        roof_spmm = {"bound": "hbm", "achieved": spmm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": spmm_gbs / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                     "kernel": "k_spmm<16,1> x3 (+ long-row reduce)", "launch_ms": t_prop_mean,
+                     "algorithmic_bytes": fwd_bytes,
+                     "no_reuse_gather_bytes": N_LAYERS * (nnz * (8 + 4 * d) + N * d * 4)}
+        roof_score = {"bound": "tensor", "achieved": score_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                      "frac": score_tf / peaks["tf_burst"], "traffic": None, "peak_source": peaks["src"] + " (burst)",
+                      "kernel": "k_score_topk_tc + merge" if mode_id else "k_score_topk_fp32 + merge",
+                      "launch_ms": t_score_mean, "algorithmic_flops": flops}
+        dominant = roof_score if t_score_mean >= t_prop_mean else roof_spmm
+        launches_per_step = N_LAYERS * (1 + (1 if g.n_long > 0 else 0)) + (2 if mode_id else 0) + 2
+        line = {
+            "metric": "users scored top-20/sec (3-layer propagation + full-catalogue scoring)",
+            "value": value, "unit": "users/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 propagation, " + {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (hi/lo split)"}[mode] + " scoring",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "n_users": nu, "m_items": mi, "edges": E, "nnz": nnz, "d": d,
+                       "layers": N_LAYERS, "k": K_TOP, "score_mode": mode, "l2": "flushed between steps (512 MB fill)",
+                       "parallelism": "1 GPU" if world_size == 1 else f"row-sharded SpMM + all-gather, item-sharded scoring x{world_size}"},
+            "spmm": {"propagated_edges_per_s": N_LAYERS * nnz / (t_prop_mean * 1e-3), "hbm_gbs": spmm_gbs,
+                     "ms": t_prop_mean, "layers": N_LAYERS},
+            "scoring": {"users_per_s": nu / (t_score_mean * 1e-3), "tflops": score_tf, "ms": t_score_mean,
+                        "pack_ms": t_pack_mean},
+            "roofline": dominant, "roofline_spmm": roof_spmm, "roofline_scoring": roof_score,
+            "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": int((nu + mi) * d * 4),
+                    "d2h_bytes_per_step": int(nu * K_TOP * 8), "ms_per_step": e2e_total / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if world_size == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_sample(shape, u, i, ue, ie)
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="amazon-book")
+    ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    from factors_of_serendipity_recommendation_b200 import synth
+    shape = synth.SHAPES[args.workload]
+    if args.impl == "reference":
+        run_reference(args, shape)
+    else:
+        run_ours(args, shape)
+
+
+if __name__ == "__main__":
+    main()

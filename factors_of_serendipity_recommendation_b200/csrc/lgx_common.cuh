@@ -63,6 +63,7 @@ struct lgx_graph {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
   int32_t n_users = 0, m_items = 0;
   int32_t chunk_nnz = 0;
+  bool values_are_dinv_products = false;  // built by lgx_graph_build from unique pairs: value == dinv[r]*dinv[c]
   int64_t n_work = 0, n_long = 0, n_partials = 0, max_row_nnz = 0;
   int64_t* indptr = nullptr;     // [n_rows + 1]
   int32_t* indices = nullptr;    // [nnz]

@@ -335,6 +335,7 @@ int lgx_graph_build(int32_t n_users, int32_t m_items, int64_t n_edges, const int
   keys = nullptr;
   g->nnz = nnz;
   const int has_dups = nnz != E2;
+  g->values_are_dinv_products = !has_dups;
   BUILD_CUDA(cudaMalloc(&g->indptr, sizeof(int64_t) * (N + 1)));
   BUILD_CUDA(cudaMalloc(&g->indices, sizeof(int32_t) * std::max<int64_t>(1, nnz)));
   BUILD_CUDA(cudaMalloc(&g->values, sizeof(float) * std::max<int64_t>(1, nnz)));

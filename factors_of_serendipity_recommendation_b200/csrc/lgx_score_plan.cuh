@@ -13,9 +13,11 @@ struct ScorePlan {
   int tiles_per_split;  // item tiles per split
 };
 
-// Pick the number of item splits so that units = n_user_tiles * n_splits fill the SMs
-// (>= units_per_sm * sms units when the batch is small; otherwise the split count in 1..8 with the
-// least last-wave waste).
+// Pick the number of item splits so that units = n_user_tiles * n_splits fill the SMs when the
+// batch alone does not.  Splits are not free: every split restarts the running top-K threshold,
+// and the number of list inserts per row grows like K*ln(items per split / K) PER SPLIT (5 splits of
+// the Amazon catalogue cost 3.9x the inserts of one pass -- measured, profiles/), so a batch with at
+// least one user tile per SM is never split.
 inline ScorePlan plan_score(int B, int M, int tile_users, int tile_items, int sms, int units_per_sm) {
   ScorePlan p;
   p.n_user_tiles = (B + tile_users - 1) / tile_users;
@@ -24,12 +26,6 @@ inline ScorePlan plan_score(int B, int M, int tile_users, int tile_items, int sm
   int splits;
   if (p.n_user_tiles >= target) {
     splits = 1;
-    double best = 1e30;
-    for (int s = 1; s <= 8; ++s) {
-      const long units = (long)p.n_user_tiles * s;
-      const double waste = (double)((units + sms - 1) / sms * sms) / (double)units;
-      if (waste < best - 0.02) { best = waste; splits = s; }
-    }
   } else {
     splits = (int)((target + p.n_user_tiles - 1) / p.n_user_tiles);
   }

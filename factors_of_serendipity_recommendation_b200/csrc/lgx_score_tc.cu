@@ -131,6 +131,7 @@ constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 struct TcParams {
   int B, M, K;            // users in batch, local items, top-K
   int k_blocks, stages;   // 64-wide K blocks per tile, B-operand ring depth
+  int q_cap;              // per-thread candidate queue capacity (multiple of 8)
   int n_splits, tiles_per_split;
   int64_t item_offset;
   TrainMask mask;
@@ -139,24 +140,107 @@ struct TcParams {
   int32_t* ws_idx;
 };
 
-// Check one 32-column chunk against the row threshold; insert survivors.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int j0, float& thresh, const TcParams& p,
-                                          int64_t uid, float* lval, int32_t* lidx) {
-  float m = __uint_as_float(v[0]);
+// Monotone cursor over one user's sorted train-item list (the user row of the bipartite CSR).
+// Item tiles are visited in ascending order, so "is this column a train item" is a compare against
+// the next pending train item instead of a binary search per candidate.
+struct TrainCursor {
+  const int32_t* idx;   // CSR column array
+  int64_t cur, end;
+  int32_t bias;         // n_users + item_offset: column value of local item 0
+  int32_t next;         // local id of the next train item, INT32_MAX when exhausted
+  __device__ __forceinline__ void init(const TrainMask& m, int64_t uid, int64_t item_offset, int first_local) {
+    idx = m.indices; cur = end = 0; next = INT32_MAX; bias = 0;
+    if (m.indptr == nullptr || uid < 0) return;
+    bias = (int32_t)(m.n_users + item_offset);
+    int64_t lo = m.indptr[uid], hi = m.indptr[uid + 1];
+    end = hi;
+    const int32_t key = bias + first_local;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(idx + mid) < key) lo = mid + 1; else hi = mid; }
+    cur = lo;
+    next = cur < end ? __ldg(idx + cur) - bias : INT32_MAX;
+  }
+  __device__ __forceinline__ void advance() {
+    ++cur;
+    next = cur < end ? __ldg(idx + cur) - bias : INT32_MAX;
+  }
+};
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Per-thread epilogue state: the row's sorted top-K list plus a small queue of pending candidates.
+// Sorted inserts are expensive and, done lane by lane inside divergent code, serialise the warp
+// (the first version spent 60% of all issued instructions there).  Candidates are therefore only
+// APPENDED in divergent code (2 stores); the queues of all 32 lanes are merged into the lists in a
+// warp-convergent flush, so the 32 insert loops run in lockstep.
+struct EpiState {
+  float thresh;      // current K-th best score of this thread's list (stale until the next flush)
+  int qn;            // pending candidates in the queue
+  float* lval; int32_t* lidx;   // list, column layout [K][256]
+  float* qval; int32_t* qidx;   // queue, column layout [q_cap][256]
+};
+
+// Kept out of line: the epilogue must stay inside the instruction cache (the fully inlined version was
+// 85 KB of SASS and 41% of its stall samples were instruction-fetch misses).  Scalars by value so the
+// caller's state stays in registers.  Returns the new threshold.
+__device__ __noinline__ float epi_flush(float* lval, int32_t* lidx, const float* qval, const int32_t* qidx, int qn,
+                                        int K, float thresh) {
+  for (int q = 0; q < qn; ++q)
+    thresh = topk_insert(lval, lidx, K, TC_EPI_THREADS, qval[q * TC_EPI_THREADS], qidx[q * TC_EPI_THREADS]);
+  __syncwarp();
+  return thresh;
+}
+
+// Check one 32-column chunk against the row threshold.
+//   rare path 1: a train item of this row falls in the chunk -> its score is overwritten with -inf
+//   fast path  : max over 4 groups of 8 columns (3-input max), one compare against the threshold
+//   rare path 2: groups whose max beats the threshold append their survivors to the queue
+__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState& st, int M, int q_cap, int K, TrainCursor& tc) {
+  if (tc.next < j0 + 32) {
+    uint32_t excl = 0;
+    do {
+      if (tc.next >= j0) excl |= 1u << (tc.next - j0);
+      tc.advance();
+    } while (tc.next < j0 + 32);
+    if (excl) {
 #pragma unroll
-  for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-  if (m > thresh) {
+      for (int i = 0; i < 32; ++i)
+        if ((excl >> i) & 1u) v[i] = 0xff800000u;   // -inf
+    }
+  }
+  float gm[4];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float s = __uint_as_float(v[i]);
-      if (s > thresh) {
-        const int j = j0 + i;
-        if (j < p.M && !p.mask.contains(uid, p.item_offset + j))
-          thresh = topk_insert(lval, lidx, p.K, TC_EPI_THREADS, s, j);
+  for (int g = 0; g < 4; ++g) {
+    const float a = max3(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+    const float b = max3(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+    gm[g] = fmaxf(max3(a, b, __uint_as_float(v[8 * g + 6])), __uint_as_float(v[8 * g + 7]));
+  }
+  const float m = fmaxf(max3(gm[0], gm[1], gm[2]), gm[3]);
+  if (__any_sync(0xffffffffu, m > st.thresh)) {        // warp-uniform
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (gm[g] > st.thresh) {                          // lane-divergent: append only
+#pragma unroll
+        for (int i = 8 * g; i < 8 * g + 8; ++i) {
+          const float s = __uint_as_float(v[i]);
+          const int j = j0 + i;
+          if (s > st.thresh && j < M) {
+            st.qval[st.qn * TC_EPI_THREADS] = s;
+            st.qidx[st.qn * TC_EPI_THREADS] = j;
+            ++st.qn;
+          }
+        }
+      }
+      __syncwarp();
+      if (__any_sync(0xffffffffu, st.qn > q_cap - 8)) {                      // warp-convergent
+        st.thresh = epi_flush(st.lval, st.lidx, st.qval, st.qidx, st.qn, K, st.thresh);
+        st.qn = 0;
       }
     }
   }
-  __syncwarp();
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -171,7 +255,10 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   const uint32_t off_lists = (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES + (uint32_t)p.stages * TC_B_STAGE_BYTES;
   float* lval_all = reinterpret_cast<float*>(gbase + off_lists);
   int32_t* lidx_all = reinterpret_cast<int32_t*>(gbase + off_lists + (size_t)p.K * TC_EPI_THREADS * 4);
-  const uint32_t off_bar = off_lists + (uint32_t)p.K * TC_EPI_THREADS * 8;
+  const uint32_t off_queue = off_lists + (uint32_t)p.K * TC_EPI_THREADS * 8;
+  float* qval_all = reinterpret_cast<float*>(gbase + off_queue);
+  int32_t* qidx_all = reinterpret_cast<int32_t*>(gbase + off_queue + (size_t)p.q_cap * TC_EPI_THREADS * 4);
+  const uint32_t off_bar = off_queue + (uint32_t)p.q_cap * TC_EPI_THREADS * 8;
   const uint32_t bar_full = base + off_bar;                     // [stages]
   const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [stages]
   const uint32_t bar_a = bar_empty + 8 * TC_MAX_STAGES;
@@ -269,11 +356,14 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     const int h = (warp - 4) >> 2;            // which 128-column half of the tile
     const int row = q * 32 + lane;            // user row inside the tile == TMEM lane
     const int col = h * TC_TILE_U + row;      // this thread's list column
-    float* lval = lval_all + col;
-    int32_t* lidx = lidx_all + col;
+    EpiState st;
+    st.thresh = -CUDART_INF_F; st.qn = 0;
+    st.lval = lval_all + col; st.lidx = lidx_all + col;
+    st.qval = qval_all + col; st.qidx = qidx_all + col;
     const int u = u_tile * TC_TILE_U + row;
     const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
-    float thresh = -CUDART_INF_F;
+    TrainCursor tcur;
+    tcur.init(p.mask, uid, p.item_offset, t_begin * TC_TILE_I);
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
       mbar_wait(bar_tfull + 8 * buf, (uint32_t)((it >> 1) & 1));
@@ -282,20 +372,22 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       const int j_base = (t_begin + it) * TC_TILE_I + h * 128;
       uint32_t va[32], vb[32];
       LGX_TMEM_LD32(va, taddr);
-      LGX_TMEM_WAIT(va);
-      LGX_TMEM_LD32(vb, taddr + 32);
-      epi_chunk(va, j_base, thresh, p, uid, lval, lidx);
-      LGX_TMEM_WAIT(vb);
-      LGX_TMEM_LD32(va, taddr + 64);
-      epi_chunk(vb, j_base + 32, thresh, p, uid, lval, lidx);
-      LGX_TMEM_WAIT(va);
-      LGX_TMEM_LD32(vb, taddr + 96);
-      epi_chunk(va, j_base + 64, thresh, p, uid, lval, lidx);
-      LGX_TMEM_WAIT(vb);
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);      // TMEM buffer may be overwritten
-      epi_chunk(vb, j_base + 96, thresh, p, uid, lval, lidx);
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {        // rolled: two chunk bodies in the instruction stream, not four
+        LGX_TMEM_WAIT(va);
+        LGX_TMEM_LD32(vb, taddr + (uint32_t)(c + 1) * 32);
+        epi_chunk(va, j_base + c * 32, st, p.M, p.q_cap, p.K, tcur);
+        LGX_TMEM_WAIT(vb);
+        if (c == 0) {
+          LGX_TMEM_LD32(va, taddr + 64);
+        } else {
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * buf);  // all four chunks are in registers: TMEM buffer may be overwritten
+        }
+        epi_chunk(vb, j_base + (c + 1) * 32, st, p.M, p.q_cap, p.K, tcur);
+      }
     }
+    st.thresh = epi_flush(st.lval, st.lidx, st.qval, st.qidx, st.qn, p.K, st.thresh);
     // merge the two column halves of every row and publish the split's partial list
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (h == 0 && u < p.B) {
@@ -351,15 +443,20 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int rows, int kto
   return LGX_OK;
 }
 
-struct TcConfig { int k_blocks, stages; size_t smem; bool ok; };
+struct TcConfig { int k_blocks, stages, q_cap; size_t smem; bool ok; };
 
 static TcConfig tc_config(int d, int K, int mode) {
   TcConfig c{};
   const int ktot = mode == LGX_SCORE_BF16X3 ? 3 * d : d;
   c.ok = (d % TC_KBLK == 0) && K >= 1 && K <= 64;
   c.k_blocks = ktot / TC_KBLK;
-  const size_t fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)K * TC_EPI_THREADS * 8 +
-                       8 * (2 * TC_MAX_STAGES + 5) + 16;
+  size_t fixed = 0;
+  for (c.q_cap = 16; c.q_cap >= 8; c.q_cap -= 8) {      // shrink the candidate queues before giving up stages
+    fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)(K + c.q_cap) * TC_EPI_THREADS * 8 +
+            8 * (2 * TC_MAX_STAGES + 5) + 16;
+    if (fixed + 3 * (size_t)TC_B_STAGE_BYTES <= TC_SMEM_LIMIT) break;
+  }
+  if (c.q_cap < 8) c.q_cap = 8;
   if (!c.ok || fixed + 2 * (size_t)TC_B_STAGE_BYTES > TC_SMEM_LIMIT) { c.ok = false; return c; }
   c.stages = (int)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / TC_B_STAGE_BYTES);
   c.smem = fixed + (size_t)c.stages * TC_B_STAGE_BYTES;
@@ -385,7 +482,7 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   if (rc != LGX_OK) return rc;
   const ScorePlan plan = tc_plan(B, M);
   TcParams p;
-  p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages;
+  p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages; p.q_cap = cfg.q_cap;
   p.n_splits = plan.n_splits; p.tiles_per_split = plan.tiles_per_split; p.item_offset = item_offset;
   p.mask = make_mask(g); p.users = users;
   p.ws_val = reinterpret_cast<float*>(workspace);

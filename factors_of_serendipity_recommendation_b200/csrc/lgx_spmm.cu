@@ -12,6 +12,7 @@
 // flight per lane.  Rows longer than chunk_nnz write per-unit partials that a second kernel sums
 // in a fixed order (deterministic, no float atomics).
 #include <algorithm>
+#include <cstdlib>
 
 #include "lgx_common.cuh"
 
@@ -50,13 +51,32 @@ __device__ __forceinline__ void epilogue4(float4 acc, int64_t off, const float* 
   }
 }
 
+__device__ __forceinline__ float4 ld_gather_f4_keep(const float* p) {   // hot row: keep in L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_gather_f4_stream(const float* p) {  // cold row: do not pollute L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
 // G lanes per work unit, V float4 per lane.  EXACT: d == 4*G*V (no column bound checks).
-template <int G, int V, bool EXACT>
-__global__ void __launch_bounds__(256)
+// U gathers in flight per lane per sub-batch; MINB resident CTAs per SM the register budget targets.
+// HOT: split the gathers by column degree -- for this graph value = dinv[row]*dinv[col], so
+// "col degree >= hot_degree" is "value <= dinv[row] / sqrt(hot_degree)"; hot rows are kept in L1
+// (evict_last), cold rows bypass it (no_allocate) so the popular rows stay resident per SM.
+template <int G, int V, bool EXACT, int U, int MINB, bool HOT>
+__global__ void __launch_bounds__(256, MINB)
 k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
        const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
-       float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d) {
-  constexpr int U = (G >= 8) ? 8 : G;  // gathers in flight per lane per sub-batch
+       float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d,
+       const float* __restrict__ dinv, float hot_rsqrt) {
+  static_assert(G % U == 0 || U > G, "U must divide G");
+  constexpr int UU = U > G ? G : U;
   const int lig = threadIdx.x & (G - 1);
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -77,37 +97,54 @@ k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, co
     int maxlen = len;  // warp-uniform trip count (groups of one warp hold neighbouring, similar-length units)
 #pragma unroll
     for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    float hot_thr = 0.f;
+    if (HOT) hot_thr = have ? __ldg(dinv + row) * hot_rsqrt : 0.f;
 
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // software pipeline: the (column, value) pair of the NEXT step is loaded while this step gathers
+    int32_t c_nxt = 0;
+    float a_nxt = 0.f;
+    if (lig < len) {
+      c_nxt = ld_stream_i32(indices + start + lig);
+      a_nxt = ld_stream_f32(values + start + lig);
+    }
     for (int base = 0; base < maxlen; base += G) {
-      const int k = base + lig;
-      int32_t c = 0;
-      float a = 0.f;
-      if (k < len) {
-        c = ld_stream_i32(indices + start + k);
-        a = ld_stream_f32(values + start + k);
+      const int32_t c = c_nxt;
+      const float a = a_nxt;
+      const int kn = base + G + lig;
+      c_nxt = 0; a_nxt = 0.f;
+      if (kn < len) {
+        c_nxt = ld_stream_i32(indices + start + kn);
+        a_nxt = ld_stream_f32(values + start + kn);
       }
       const int cnt = len - base;  // may be <= 0 for the shorter group of the warp
 #pragma unroll
-      for (int j0 = 0; j0 < G; j0 += U) {
-        float4 x[U][V];
-        float av[U];
+      for (int j0 = 0; j0 < G; j0 += UU) {
+        float4 x[UU][V];
+        float av[UU];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
+        for (int j = 0; j < UU; ++j) {
           const int32_t cj = __shfl_sync(0xffffffffu, c, j0 + j, G);
           av[j] = __shfl_sync(0xffffffffu, a, j0 + j, G);
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             x[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
             const int col4 = lig + v * G;
-            if (j0 + j < cnt && (EXACT || col4 < d4)) x[j][v] = ld_gather_f4(X + (int64_t)cj * d + (col4 << 2));
+            if (j0 + j < cnt && (EXACT || col4 < d4)) {
+              const float* src = X + (int64_t)cj * d + (col4 << 2);
+              if (HOT) {
+                if (av[j] <= hot_thr) x[j][v] = ld_gather_f4_keep(src); else x[j][v] = ld_gather_f4_stream(src);
+              } else {
+                x[j][v] = ld_gather_f4(src);
+              }
+            }
           }
         }
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
+        for (int j = 0; j < UU; ++j) {
 #pragma unroll
           for (int v = 0; v < V; ++v) fma4(acc[v], av[j], x[j][v]);
         }
@@ -207,42 +244,71 @@ static int blocks_for(K kernel, int threads) {
   return per_sm * sm_count();
 }
 
-template <int G, int V, bool EXACT>
+struct SpmmTuning {
+  int variant;      // kernel variant for d = 64 (see spmm_impl)
+  int hot_degree;   // columns with at least this degree are kept in L1 (HOT variants)
+};
+static SpmmTuning tuning() {
+  static SpmmTuning t = [] {
+    SpmmTuning x{0, 256};
+    if (const char* e = getenv("LGX_SPMM_VARIANT")) x.variant = atoi(e);
+    if (const char* e = getenv("LGX_SPMM_HOT_DEGREE")) x.hot_degree = std::max(1, atoi(e));
+    return x;
+  }();
+  return t;
+}
+
+template <int G, int V, bool EXACT, int U, int MINB, bool HOT>
 static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
                         float div, int d, cudaStream_t st) {
   static int max_blocks = 0;
-  if (max_blocks == 0) max_blocks = blocks_for(k_spmm<G, V, EXACT>, 256);
+  if (max_blocks == 0) max_blocks = blocks_for(k_spmm<G, V, EXACT, U, MINB, HOT>, 256);
   const int64_t groups_per_block = 256 / G;
   const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
-  k_spmm<G, V, EXACT><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial,
-                                              div, d);
+  const float hot_rsqrt = 1.0f / sqrtf((float)tuning().hot_degree);
+  k_spmm<G, V, EXACT, U, MINB, HOT><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values,
+                                                           X, S_in, Y, S_out, partial, div, d, g->dinv, hot_rsqrt);
 }
 
 static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div,
                      int32_t d, void* workspace, cudaStream_t st) {
   float* partial = reinterpret_cast<float*>(workspace);
   if (g->n_work > 0) {
+    const bool hot_ok = g->values_are_dinv_products;   // HOT needs value == dinv[row]*dinv[col]
     if (d % 4 != 0) {
       const int64_t need = (g->n_work + 7) / 8;
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
       k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d);
     } else if (d == 64) {
-      launch_spmm<16, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+      switch (tuning().variant) {
+        case 1: launch_spmm<16, 1, true, 8, 3, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 3: launch_spmm<16, 1, true, 16, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 4: launch_spmm<16, 1, true, 8, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 5: if (hot_ok) { launch_spmm<16, 1, true, 8, 2, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
+        case 6: if (hot_ok) { launch_spmm<16, 1, true, 8, 3, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
+        case 7: if (hot_ok) { launch_spmm<16, 1, true, 4, 4, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
+        case 8: launch_spmm<16, 1, true, 4, 5, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 9: launch_spmm<16, 1, true, 2, 6, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 10: launch_spmm<16, 1, true, 4, 6, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 11: launch_spmm<16, 1, true, 2, 8, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 12: launch_spmm<16, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        default: launch_spmm<16, 1, true, 4, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+      }
     } else if (d == 128) {
-      launch_spmm<32, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     } else if (d == 256) {
-      launch_spmm<32, 2, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 2, true, 8, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     } else if (d == 32) {
-      launch_spmm<8, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<8, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     } else if (d == 16) {
-      launch_spmm<4, 1, true>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<4, 1, true, 4, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     } else if (d <= 128) {
-      launch_spmm<32, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 1, false, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     } else if (d <= 256) {
-      launch_spmm<32, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 2, false, 8, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     } else {
-      launch_spmm<32, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 4, false, 4, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
     }
     LGX_CHECK_LAUNCH();
   }
