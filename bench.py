@@ -203,7 +203,7 @@ def run_ours(args, shape):
     def step_resident():
         """inputs resident in HBM; returns event triplet timings handled by the caller"""
         if engine is not None:
-            return engine.step(E0, all_users, K_TOP, mode_id)
+            return engine.step(E0, all_users, K_TOP, mode_id, shard=args.shard)
         g.propagate_fwd(E0, N_LAYERS, out=light)
         au, ai = light[:nu], light[nu:]
         if mode_id == _lgx.SCORE_FP32:
@@ -218,7 +218,7 @@ def run_ours(args, shape):
         flush.fill_(1)                                        # evict L2 between timed iterations
         if engine is not None:
             ev[0].record()
-            engine.step(E0, all_users, K_TOP, mode_id, events=ev)
+            engine.step(E0, all_users, K_TOP, mode_id, events=ev, shard=args.shard)
             ev[3].record()
             return ev
         ev[0].record()
@@ -276,7 +276,7 @@ def run_ours(args, shape):
         m.embedding_item.weight.data.copy_(host_i, non_blocking=True)
         m._eval_cache = None
         if engine is not None:
-            idx, _ = engine.step(m._flat_if_fused(), all_users, K_TOP, mode_id)
+            idx, _ = engine.step(m._flat_if_fused(), all_users, K_TOP, mode_id, shard=args.shard)
         else:
             idx, _ = m.topk(all_users, K_TOP, mode=mode)      # the call a user makes (computer() inside)
         host_out.copy_(idx, non_blocking=True)
@@ -320,7 +320,8 @@ def run_ours(args, shape):
             "data": "synthetic",
             "config": {"workload": args.workload, "n_users": nu, "m_items": mi, "edges": E, "nnz": nnz, "d": d,
                        "layers": N_LAYERS, "k": K_TOP, "score_mode": mode, "l2": "flushed between steps (512 MB fill)",
-                       "parallelism": "1 GPU" if world_size == 1 else f"row-sharded SpMM + all-gather, item-sharded scoring x{world_size}"},
+                       "parallelism": "1 GPU" if world_size == 1 else
+                       f"row-sharded SpMM + NCCL all-gather per layer, scoring sharded by {args.shard} x{world_size}"},
             "spmm": {"propagated_edges_per_s": N_LAYERS * nnz / (t_prop_mean * 1e-3), "hbm_gbs": spmm_gbs,
                      "ms": t_prop_mean, "layers": N_LAYERS},
             "scoring": {"users_per_s": nu / (t_score_mean * 1e-3), "tflops": score_tf, "ms": t_score_mean,
@@ -347,6 +348,7 @@ def main():
     ap.add_argument("--workload", default="amazon-book")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"], help="scoring split at N > 1")
     args = ap.parse_args()
     from factors_of_serendipity_recommendation_b200 import synth
     shape = synth.SHAPES[args.workload]

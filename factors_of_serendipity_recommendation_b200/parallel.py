@@ -1,0 +1,180 @@
+"""Multi-GPU LightGCN: row-sharded propagation + item-sharded scoring, one process per GPU.
+
+The reference has no distributed code; its only scaling mechanism is the (disabled) sequential
+row-fold split ``_split_A_hat`` + ``torch.cat`` (PT/dataloader.py:319-329, PT/model.py:164-169).  This
+module is that pattern across GPUs: every rank owns a block of CSR rows, computes its rows of the
+next layer with the same fused SpMM kernel, and one NCCL all-gather per layer (the ``torch.cat``)
+rebuilds the full layer on every rank.  Scoring shards the item catalogue; the per-rank top-K lists
+are all-gathered ([B, K] per rank) and merged with lgx_topk_merge.
+
+Row partition: contiguous folds are badly imbalanced on power-law graphs, so rows are dealt
+round-robin over the degree-sorted order (rank = position % P).  Every rank gets the same number of
+rows (padded) and near-equal nnz.  Node ids are relabelled so that the all-gathered buffer is
+directly indexable: new_id = rank * n_local + local_index.  No permutation pass per layer.
+
+The partition functions below are pure index arithmetic on torch tensors (CPU or CUDA) so the
+N > 1 plumbing is testable with gloo on CPU; all arithmetic on embeddings goes through liblgx.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def partition_rows(row_order: torch.Tensor, world: int):
+    """row_order: stable degree-descending row ids [N].  -> (n_local, new_id [N], old_of_new [world*n_local])
+    new_id[r]  = position of global row r in the all-gathered layout (rank-major);
+    old_of_new = inverse map, -1 for padding slots."""
+    N = row_order.numel()
+    n_local = (N + world - 1) // world
+    pos = torch.arange(N, device=row_order.device, dtype=torch.int64)
+    new_of_pos = (pos % world) * n_local + pos // world
+    new_id = torch.empty(N, dtype=torch.int64, device=row_order.device)
+    new_id[row_order.long()] = new_of_pos
+    old_of_new = torch.full((world * n_local,), -1, dtype=torch.int64, device=row_order.device)
+    old_of_new[new_of_pos] = row_order.long()
+    return n_local, new_id, old_of_new
+
+
+def shard_csr(indptr, indices, values, row_order, rank: int, world: int):
+    """This rank's row block of the canonical CSR with columns relabelled to the gathered layout.
+    -> (indptr_local int64 [n_local+1], cols int32 [nnz_local], vals f32 [nnz_local], n_local, new_id, old_of_new)"""
+    n_local, new_id, old_of_new = partition_rows(row_order, world)
+    mine = old_of_new[rank * n_local:(rank + 1) * n_local]           # global row ids, -1 = padding
+    valid = mine >= 0
+    rows = mine.clamp(min=0)
+    lens = (indptr[rows + 1] - indptr[rows]) * valid
+    local_ptr = torch.zeros(n_local + 1, dtype=torch.int64, device=indptr.device)
+    local_ptr[1:] = torch.cumsum(lens, 0)
+    total = int(local_ptr[-1])
+    seg = torch.repeat_interleave(indptr[rows] - local_ptr[:-1], lens)
+    src = seg + torch.arange(total, device=indptr.device, dtype=torch.int64)
+    cols = new_id[indices[src].long()].to(torch.int32)
+    vals = values[src]
+    return local_ptr, cols, vals, n_local, new_id, old_of_new
+
+
+def item_shard_bounds(m_items: int, rank: int, world: int):
+    per = (m_items + world - 1) // world
+    lo = min(m_items, rank * per)
+    return lo, min(m_items, lo + per)
+
+
+def merge_candidates_reference(cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int):
+    """Index arithmetic of lgx_topk_merge in torch ([P, B, k] -> [B, k]; score desc, ties by lower id):
+    used by the CPU gloo test to check the exchange, never by the product path."""
+    P, B, kk = cand_idx.shape
+    idx = cand_idx.permute(1, 0, 2).reshape(B, P * kk)
+    val = cand_val.permute(1, 0, 2).reshape(B, P * kk)
+    order = torch.argsort(idx, dim=1, stable=True)
+    idx, val = torch.gather(idx, 1, order), torch.gather(val, 1, order)
+    order = torch.argsort(val, dim=1, descending=True, stable=True)
+    return torch.gather(idx, 1, order)[:, :k], torch.gather(val, 1, order)[:, :k]
+
+
+class ShardedEngine:
+    """Forward propagation + full-catalogue top-K over ``world`` GPUs (one instance per rank)."""
+
+    def __init__(self, graph, n_users: int, m_items: int, d: int, n_layers: int, rank: int, world: int, device):
+        from . import _lgx
+
+        self._lgx = _lgx
+        self.g_full = graph                       # replicated canonical graph: train mask + original ids
+        self.n_users, self.m_items, self.d, self.L = n_users, m_items, d, n_layers
+        self.rank, self.world, self.dev = rank, world, device
+        e = graph.export()
+        ptr, cols, vals, self.n_local, self.new_id, self.old_of_new = shard_csr(
+            e["indptr"], e["indices"], e["values"], e["row_order"], rank, world)
+        self.local = _lgx.Graph.from_csr(ptr, cols, vals, n_cols=world * self.n_local, n_users=0, m_items=0)
+        self.gather_src = self.old_of_new.clamp(min=0)
+        self.pad_mask = (self.old_of_new < 0)
+        self.has_pad = bool(self.pad_mask.any().item())
+        n_tot = world * self.n_local
+        self.X = [torch.zeros(n_tot, d, device=device) for _ in range(2)]       # gathered layers (ping-pong)
+        self.Y = torch.empty(self.n_local, d, device=device)                    # my rows of the next layer
+        self.S = torch.empty(self.n_local, d, device=device)                    # my rows of the running sum
+        self.full_mean = torch.empty(n_tot, d, device=device)
+        self.lo, self.hi = item_shard_bounds(m_items, rank, world)
+
+    def propagate(self, E0: torch.Tensor) -> torch.Tensor:
+        """E0 [N, d] (original order, replicated) -> light_out [N, d] (original order, replicated)."""
+        L, nl, r = self.L, self.n_local, self.rank
+        X0 = self.X[0]
+        torch.index_select(E0, 0, self.gather_src, out=X0)
+        if self.has_pad:
+            X0[self.pad_mask] = 0
+        if L == 0:
+            return E0.clone()
+        cur = 0
+        S_in = X0[r * nl:(r + 1) * nl]
+        for l in range(1, L + 1):
+            last = l == L
+            self.local.spmm(self.X[cur], S_in=S_in, Y=None if last else self.Y, S_out=self.S,
+                            div=float(L + 1) if last else 1.0)
+            if not last:
+                dist.all_gather_into_tensor(self.X[1 - cur], self.Y)              # the reference's torch.cat of folds
+                cur = 1 - cur
+            S_in = self.S
+        dist.all_gather_into_tensor(self.full_mean, self.S)
+        return self.full_mean.index_select(0, self.new_id)
+
+    def score(self, light: torch.Tensor, users: torch.Tensor, k: int, mode_id: int, shard: str = "items"):
+        """Top-k for ``users`` (replicated list) on every rank.
+
+        shard="items": each rank scores ALL users against its slice of the catalogue, the [B, k] candidate
+                       lists are all-gathered and merged (the exchange BASELINE.json names; needed when the
+                       catalogue itself is what must be split, e.g. 2M items x d=256).
+        shard="users": each rank scores its slice of the users against the whole catalogue; results are
+                       all-gathered, no merge.  The fused kernel is bound by its top-K epilogue, whose
+                       insert count per row ~ K*ln(items/K) barely shrinks with the item slice, so this is
+                       the split that scales when the catalogue fits one GPU (measured: DESIGN.md).
+        shard="auto" : users when every rank still gets >= 1 tile of 128 users, else items."""
+        _lgx = self._lgx
+        B = users.numel()
+        if shard == "auto":
+            shard = "users" if B >= self.world * 128 else "items"
+        au, ai = light[: self.n_users], light[self.n_users:]
+        if shard == "users":
+            per = (B + self.world - 1) // self.world
+            lo, hi = min(B, self.rank * per), min(B, (self.rank + 1) * per)
+            idx = torch.full((per, k), -1, dtype=torch.int64, device=self.dev)
+            val = torch.full((per, k), float("-inf"), device=self.dev)
+            if hi > lo:
+                mine = users[lo:hi].contiguous()
+                if mode_id == _lgx.SCORE_FP32:
+                    U_op, I_op = au.index_select(0, mine), ai.contiguous()
+                else:
+                    U_op = _lgx.pack_operand(au, mine, mode_id, False)
+                    I_op = _lgx.pack_operand(ai.contiguous(), None, mode_id, True)
+                i2, v2 = _lgx.score_topk(self.g_full, U_op, mine, I_op, self.d, k, mode_id)
+                idx[: hi - lo], val[: hi - lo] = i2, v2
+            all_idx = torch.empty(self.world * per, k, dtype=torch.int64, device=self.dev)
+            all_val = torch.empty(self.world * per, k, dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(all_idx, idx)
+            dist.all_gather_into_tensor(all_val, val)
+            return all_idx[:B], all_val[:B]
+        shard_items = ai[self.lo:self.hi]
+        kk = min(k, self.hi - self.lo)
+        if mode_id == _lgx.SCORE_FP32:
+            U_op, I_op = au.index_select(0, users), shard_items.contiguous()
+        else:
+            U_op = _lgx.pack_operand(au, users, mode_id, False)
+            I_op = _lgx.pack_operand(shard_items.contiguous(), None, mode_id, True)
+        idx, val = _lgx.score_topk(self.g_full, U_op, users, I_op, self.d, kk, mode_id, item_offset=self.lo)
+        if kk < k:
+            pad_i = torch.full((B, k), -1, dtype=torch.int64, device=self.dev)
+            pad_v = torch.full((B, k), float("-inf"), device=self.dev)
+            pad_i[:, :kk], pad_v[:, :kk] = idx, val
+            idx, val = pad_i, pad_v
+        all_idx = torch.empty(self.world, B, k, dtype=torch.int64, device=self.dev)
+        all_val = torch.empty(self.world, B, k, dtype=torch.float32, device=self.dev)
+        dist.all_gather_into_tensor(all_idx, idx.contiguous())
+        dist.all_gather_into_tensor(all_val, val.contiguous())
+        return _lgx.topk_merge(all_idx, all_val)
+
+    def step(self, E0, users, k, mode_id, events=None, shard: str = "auto"):
+        light = self.propagate(E0)
+        if events is not None:
+            events[1].record()
+            events[2].record()
+        return self.score(light, users, k, mode_id, shard=shard)

@@ -1,0 +1,58 @@
+"""ShardedEngine (row-sharded SpMM + NCCL all-gather, item-sharded top-K + merge) vs the 1-GPU path.
+Runs with as many ranks as there are GPUs on the box (1 on the default GPU test box, 2+ under
+`gpurun --gpus N`); the world-size-2 plumbing is also covered on CPU by tests/test_parallel_cpu.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from factors_of_serendipity_recommendation_b200 import _lgx, dataloader, model, parallel, synth, world as W
+    nu, mi, d, L, k = 1501, 2222, 64, 3, 20
+    u, i = synth.make_interactions(nu, mi, 40000, seed=5)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=5, trained_like=True)
+    cfg = dict(W.config)
+    cfg.update(pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy(), lightGCN_n_layers=L)
+    ds = dataloader.InteractionDataset(nu, mi, u, i, device=dev)
+    m = model.LightGCN(cfg, ds).to(dev).eval()
+    g = ds.getGraphHandle()
+    eng = parallel.ShardedEngine(g, nu, mi, d, L, rank, world, dev)
+    E0 = m._flat_if_fused()
+    users = torch.arange(nu, device=dev)
+    with torch.no_grad():
+        lu, li = m.computer()
+        light = eng.propagate(E0)
+        ref = torch.cat([lu, li])
+        assert (light - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+        for mode in ("fp32", "bf16x3"):
+            idx1, val1 = m.topk(users, k, mode=mode)
+            for shard in ("items", "users"):
+                idxN, valN = eng.score(ref, users, k, _lgx.MODES[mode], shard=shard)   # same embeddings -> identical lists
+                assert torch.equal(idx1, idxN) and torch.equal(val1, valN), (mode, shard)
+        idx, val = eng.step(E0, users, k, _lgx.MODES["bf16x3"])
+        same = (idx == m.topk(users, k, mode="bf16x3")[0]).float().mean().item()
+        assert same > 0.999                                               # propagate differs in the last ulp only
+    torch.cuda.synchronize()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_engine_matches_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    world = min(2, torch.cuda.device_count())
+    port = 29600 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

@@ -1,0 +1,104 @@
+"""N > 1 plumbing on CPU: world_size-2 gloo processes run the row partition, the per-layer all-gather
+and the item-sharded top-K exchange of parallel.py.  The embedding arithmetic is done here with torch
+CPU ops (a test double for the CUDA kernels); what is under test is the sharding/relabelling/exchange."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from factors_of_serendipity_recommendation_b200 import parallel, synth
+    from oracle import lightgcn_oracle as O
+
+    nu, mi, d, L, k = 151, 222, 16, 3, 10                     # N = 373: odd -> one padding row at world 2
+    u, i = synth.make_interactions(nu, mi, 4000, seed=5)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=5, trained_like=True)
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=L, user_emb=ue, item_emb=ie)
+    indptr = torch.from_numpy(ref.indptr)
+    indices = torch.from_numpy(ref.indices)
+    values = torch.from_numpy(ref.data)
+    order = torch.from_numpy(O.degree_sorted_row_order(ref.degree, ref.indptr))
+    N = nu + mi
+
+    ptr, cols, vals, n_local, new_id, old_of_new = parallel.shard_csr(indptr, indices, values, order, rank, world)
+    # partition invariants
+    assert n_local == (N + world - 1) // world
+    assert torch.equal(old_of_new[new_id], torch.arange(N))
+    mine = old_of_new[rank * n_local:(rank + 1) * n_local]
+    assert torch.equal(mine[mine >= 0], order.long()[rank::world])
+    nnz_all = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(nnz_all, torch.tensor([cols.numel()]))
+    assert sum(int(x) for x in nnz_all) == indices.numel()
+    assert max(int(x) for x in nnz_all) <= 1.15 * indices.numel() / world       # degree-cyclic deal balances nnz
+
+    A_local = torch.sparse_csr_tensor(ptr, cols.long(), vals, (n_local, world * n_local))
+    E0 = torch.cat([ue, ie])
+    X = torch.zeros(world * n_local, d)
+    X[new_id] = E0
+    S = X[rank * n_local:(rank + 1) * n_local].clone()
+    for l in range(L):
+        Y = A_local @ X
+        S = S + Y
+        parts = [torch.empty_like(Y) for _ in range(world)]
+        dist.all_gather(parts, Y)
+        X = torch.cat(parts)
+    S = S / (L + 1)
+    parts = [torch.empty_like(S) for _ in range(world)]
+    dist.all_gather(parts, S)
+    light = torch.cat(parts)[new_id]
+    with torch.no_grad():
+        ru, ri = ref.computer()
+    full = torch.cat([ru, ri])
+    assert (light - full).abs().max() <= 1e-5 * full.abs().max()
+
+    # item-sharded scoring + candidate exchange
+    lo, hi = parallel.item_shard_bounds(mi, rank, world)
+    users = torch.arange(nu)
+    score = (light[:nu] @ light[nu:][lo:hi].t())
+    for r, items in enumerate(ref.all_pos(users.numpy())):
+        sel = items[(items >= lo) & (items < hi)] - lo
+        score[r, sel] = float("-inf")
+    v, ix = torch.topk(score, k)
+    cand_i = [torch.empty_like(ix) for _ in range(world)]
+    cand_v = [torch.empty_like(v) for _ in range(world)]
+    dist.all_gather(cand_i, ix + lo)
+    dist.all_gather(cand_v, v)
+    midx, mval = parallel.merge_candidates_reference(torch.stack(cand_i), torch.stack(cand_v), k)
+    s_full = (full[:nu].double() @ full[nu:].double().t()).numpy()
+    for r, items in enumerate(ref.all_pos(users.numpy())):
+        s_full[r, items] = -np.inf
+    scale = np.abs(s_full[np.isfinite(s_full)]).max()
+    assert all(O.topk_is_valid(s_full[r], midx[r].numpy(), k, tol=1e-5 * scale) for r in range(nu))
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_row_sharded_propagation_and_item_sharded_topk_gloo(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_partition_and_merge_single_process():
+    sys.path.insert(0, REPO)
+    from factors_of_serendipity_recommendation_b200 import parallel
+    order = torch.tensor([4, 0, 2, 1, 3], dtype=torch.int32)
+    n_local, new_id, old = parallel.partition_rows(order, 2)
+    assert n_local == 3 and old.tolist() == [4, 2, 3, 0, 1, -1] and new_id.tolist() == [3, 4, 1, 2, 0]
+    assert parallel.item_shard_bounds(10, 0, 4) == (0, 3) and parallel.item_shard_bounds(10, 3, 4) == (9, 10)
+    ci = torch.tensor([[[5, 1]], [[7, 9]]])
+    cv = torch.tensor([[[2.0, 1.0]], [[2.0, 0.5]]])
+    idx, val = parallel.merge_candidates_reference(ci, cv, 3)
+    assert idx.tolist() == [[5, 7, 1]] and val.tolist() == [[2.0, 2.0, 1.0]]
