@@ -171,34 +171,54 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return r;
 }
 
-// Per-thread epilogue state: the row's sorted top-K list plus a small queue of pending candidates.
-// Sorted inserts are expensive and, done lane by lane inside divergent code, serialise the warp
-// (the first version spent 60% of all issued instructions there).  Candidates are therefore only
-// APPENDED in divergent code (2 stores); the queues of all 32 lanes are merged into the lists in a
-// warp-convergent flush, so the 32 insert loops run in lockstep.
+// Per-thread epilogue state.
+//  * the row's top-K list lives in REGISTERS (KMAX slots, sorted best-first, right-aligned: slots
+//    [0, KMAX-K) hold +inf sentinels so the K-th best is always the last slot).  One insert is a
+//    branch-free sweep in which every slot is computed from the OLD neighbours -- no dependency chain,
+//    no shared-memory latency (the shared-memory list version spent 30% of the epilogue there);
+//  * candidates are only APPENDED (2 stores to a shared-memory queue) inside divergent code; the 32
+//    lanes' queues are merged into the lists in a warp-convergent flush, so inserts run in lockstep.
+template <int KMAX>
 struct EpiState {
-  float thresh;      // current K-th best score of this thread's list (stale until the next flush)
-  int qn;            // pending candidates in the queue
-  float* lval; int32_t* lidx;   // list, column layout [K][256]
+  float lv[KMAX];
+  int32_t li[KMAX];
+  int qn;                       // pending candidates in the queue
   float* qval; int32_t* qidx;   // queue, column layout [q_cap][256]
+  __device__ __forceinline__ float thresh() const { return lv[KMAX - 1]; }
+  __device__ __forceinline__ void init(int K) {
+#pragma unroll
+    for (int p = 0; p < KMAX; ++p) {
+      lv[p] = p < KMAX - K ? CUDART_INF_F : -CUDART_INF_F;
+      li[p] = INT32_MAX;
+    }
+    qn = 0;
+  }
+  // Items reach a thread in ascending id order, so an equal score always loses the tie: strict '>'.
+  __device__ __forceinline__ void insert(float x, int32_t xi) {
+#pragma unroll
+    for (int p = KMAX - 1; p >= 1; --p) {
+      const bool gp = x > lv[p], gq = x > lv[p - 1];
+      lv[p] = gp ? (gq ? lv[p - 1] : x) : lv[p];
+      li[p] = gp ? (gq ? li[p - 1] : xi) : li[p];
+    }
+    const bool g0 = x > lv[0];
+    lv[0] = g0 ? x : lv[0];
+    li[0] = g0 ? xi : li[0];
+  }
+  __device__ __forceinline__ void flush() {
+    for (int q = 0; q < qn; ++q) insert(qval[q * TC_EPI_THREADS], qidx[q * TC_EPI_THREADS]);
+    qn = 0;
+    __syncwarp();
+  }
 };
-
-// Kept out of line: the epilogue must stay inside the instruction cache (the fully inlined version was
-// 85 KB of SASS and 41% of its stall samples were instruction-fetch misses).  Scalars by value so the
-// caller's state stays in registers.  Returns the new threshold.
-__device__ __noinline__ float epi_flush(float* lval, int32_t* lidx, const float* qval, const int32_t* qidx, int qn,
-                                        int K, float thresh) {
-  for (int q = 0; q < qn; ++q)
-    thresh = topk_insert(lval, lidx, K, TC_EPI_THREADS, qval[q * TC_EPI_THREADS], qidx[q * TC_EPI_THREADS]);
-  __syncwarp();
-  return thresh;
-}
 
 // Check one 32-column chunk against the row threshold.
 //   rare path 1: a train item of this row falls in the chunk -> its score is overwritten with -inf
 //   fast path  : max over 4 groups of 8 columns (3-input max), one compare against the threshold
 //   rare path 2: groups whose max beats the threshold append their survivors to the queue
-__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState& st, int M, int q_cap, int K, TrainCursor& tc) {
+template <int KMAX, bool SMALLQ>
+__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KMAX>& st, int M, int q_cap,
+                                          TrainCursor& tc) {
   if (tc.next < j0 + 32) {
     uint32_t excl = 0;
     do {
@@ -219,30 +239,35 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState& s
     gm[g] = fmaxf(max3(a, b, __uint_as_float(v[8 * g + 6])), __uint_as_float(v[8 * g + 7]));
   }
   const float m = fmaxf(max3(gm[0], gm[1], gm[2]), gm[3]);
-  if (__any_sync(0xffffffffu, m > st.thresh)) {        // warp-uniform
+  const float th = st.thresh();
+  if (__any_sync(0xffffffffu, m > th)) {               // warp-uniform
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      if (gm[g] > st.thresh) {                          // lane-divergent: append only
+      if (gm[g] > th) {                                 // lane-divergent: append only
 #pragma unroll
         for (int i = 8 * g; i < 8 * g + 8; ++i) {
           const float s = __uint_as_float(v[i]);
           const int j = j0 + i;
-          if (s > st.thresh && j < M) {
+          if (s > th && j < M) {
             st.qval[st.qn * TC_EPI_THREADS] = s;
             st.qidx[st.qn * TC_EPI_THREADS] = j;
             ++st.qn;
           }
         }
       }
-      __syncwarp();
-      if (__any_sync(0xffffffffu, st.qn > q_cap - 8)) {                      // warp-convergent
-        st.thresh = epi_flush(st.lval, st.lidx, st.qval, st.qidx, st.qn, K, st.thresh);
-        st.qn = 0;
+      if (SMALLQ) {                                     // small queues (big user tile in smem): check per group
+        __syncwarp();
+        if (__any_sync(0xffffffffu, st.qn > q_cap - 8)) st.flush();
       }
+    }
+    if (!SMALLQ) {
+      __syncwarp();
+      if (__any_sync(0xffffffffu, st.qn > q_cap - 32)) st.flush();   // warp-convergent
     }
   }
 }
 
+template <int KMAX, bool SMALLQ>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_i,
                 const TcParams p) {
@@ -252,10 +277,11 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   unsigned char* gbase = smem_dyn + (base - raw);
   const uint32_t sA = base;
   const uint32_t sB = sA + (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES;
-  const uint32_t off_lists = (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES + (uint32_t)p.stages * TC_B_STAGE_BYTES;
-  float* lval_all = reinterpret_cast<float*>(gbase + off_lists);
-  int32_t* lidx_all = reinterpret_cast<int32_t*>(gbase + off_lists + (size_t)p.K * TC_EPI_THREADS * 4);
-  const uint32_t off_queue = off_lists + (uint32_t)p.K * TC_EPI_THREADS * 8;
+  const uint32_t off_stages = (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES;
+  const uint32_t off_queue = off_stages + (uint32_t)p.stages * TC_B_STAGE_BYTES;
+  // final lists are staged over the (then idle) B-operand ring: KMAX*256*8 <= 64 KB <= 2 stages
+  float* lval_all = reinterpret_cast<float*>(gbase + off_stages);
+  int32_t* lidx_all = reinterpret_cast<int32_t*>(gbase + off_stages + (size_t)KMAX * TC_EPI_THREADS * 4);
   float* qval_all = reinterpret_cast<float*>(gbase + off_queue);
   int32_t* qidx_all = reinterpret_cast<int32_t*>(gbase + off_queue + (size_t)p.q_cap * TC_EPI_THREADS * 4);
   const uint32_t off_bar = off_queue + (uint32_t)p.q_cap * TC_EPI_THREADS * 8;
@@ -292,13 +318,6 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 4) {
-    const int col = threadIdx.x - 128;
-    for (int k = 0; k < p.K; ++k) {
-      lval_all[k * TC_EPI_THREADS + col] = -CUDART_INF_F;
-      lidx_all[k * TC_EPI_THREADS + col] = INT32_MAX;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -356,9 +375,8 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     const int h = (warp - 4) >> 2;            // which 128-column half of the tile
     const int row = q * 32 + lane;            // user row inside the tile == TMEM lane
     const int col = h * TC_TILE_U + row;      // this thread's list column
-    EpiState st;
-    st.thresh = -CUDART_INF_F; st.qn = 0;
-    st.lval = lval_all + col; st.lidx = lidx_all + col;
+    EpiState<KMAX> st;
+    st.init(p.K);
     st.qval = qval_all + col; st.qidx = qidx_all + col;
     const int u = u_tile * TC_TILE_U + row;
     const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
@@ -376,7 +394,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       for (int c = 0; c < 4; c += 2) {        // rolled: two chunk bodies in the instruction stream, not four
         LGX_TMEM_WAIT(va);
         LGX_TMEM_LD32(vb, taddr + (uint32_t)(c + 1) * 32);
-        epi_chunk(va, j_base + c * 32, st, p.M, p.q_cap, p.K, tcur);
+        epi_chunk<KMAX, SMALLQ>(va, j_base + c * 32, st, p.M, p.q_cap, tcur);
         LGX_TMEM_WAIT(vb);
         if (c == 0) {
           LGX_TMEM_LD32(va, taddr + 64);
@@ -384,16 +402,23 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
           tc_fence_before();
           mbar_arrive(bar_tempty + 8 * buf);  // all four chunks are in registers: TMEM buffer may be overwritten
         }
-        epi_chunk(vb, j_base + (c + 1) * 32, st, p.M, p.q_cap, p.K, tcur);
+        epi_chunk<KMAX, SMALLQ>(vb, j_base + (c + 1) * 32, st, p.M, p.q_cap, tcur);
       }
     }
-    st.thresh = epi_flush(st.lval, st.lidx, st.qval, st.qidx, st.qn, p.K, st.thresh);
-    // merge the two column halves of every row and publish the split's partial list
+    st.flush();
+    // stage the register lists (the B ring is idle: every MMA of this unit has retired), merge the
+    // two column halves of every row and publish the split's partial list
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      lval_all[k * TC_EPI_THREADS + col] = st.lv[k];
+      lidx_all[k * TC_EPI_THREADS + col] = st.li[k];
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (h == 0 && u < p.B) {
+      const int k0 = KMAX - p.K;                 // lists are right-aligned in their KMAX slots
       const float* v0 = lval_all + row;  const int32_t* i0 = lidx_all + row;
       const float* v1 = lval_all + TC_TILE_U + row;  const int32_t* i1 = lidx_all + TC_TILE_U + row;
-      int a = 0, b = 0;
+      int a = k0, b = k0;
       const int64_t o = ((int64_t)split * p.B + u) * p.K;
       for (int k = 0; k < p.K; ++k) {
         const float fa = v0[a * TC_EPI_THREADS], fb = v1[b * TC_EPI_THREADS];
@@ -448,15 +473,15 @@ struct TcConfig { int k_blocks, stages, q_cap; size_t smem; bool ok; };
 static TcConfig tc_config(int d, int K, int mode) {
   TcConfig c{};
   const int ktot = mode == LGX_SCORE_BF16X3 ? 3 * d : d;
-  c.ok = (d % TC_KBLK == 0) && K >= 1 && K <= 64;
+  c.ok = (d % TC_KBLK == 0) && K >= 1 && K <= 32;
   c.k_blocks = ktot / TC_KBLK;
   size_t fixed = 0;
-  for (c.q_cap = 16; c.q_cap >= 8; c.q_cap -= 8) {      // shrink the candidate queues before giving up stages
-    fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)(K + c.q_cap) * TC_EPI_THREADS * 8 +
+  for (c.q_cap = 40; c.q_cap >= 16; c.q_cap -= 24) {    // shrink the candidate queues before giving up stages
+    fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)c.q_cap * TC_EPI_THREADS * 8 +
             8 * (2 * TC_MAX_STAGES + 5) + 16;
     if (fixed + 3 * (size_t)TC_B_STAGE_BYTES <= TC_SMEM_LIMIT) break;
   }
-  if (c.q_cap < 8) c.q_cap = 8;
+  if (c.q_cap < 16) c.q_cap = 16;
   if (!c.ok || fixed + 2 * (size_t)TC_B_STAGE_BYTES > TC_SMEM_LIMIT) { c.ok = false; return c; }
   c.stages = (int)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / TC_B_STAGE_BYTES);
   c.smem = fixed + (size_t)c.stages * TC_B_STAGE_BYTES;
@@ -470,7 +495,7 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
                          void* workspace, cudaStream_t st) {
   const TcConfig cfg = tc_config(d, K, mode);
   if (!cfg.ok) {
-    set_error("tcgen05 scoring needs d % 64 == 0, k <= 64 and the user tile + 2 item stages to fit in 227 KB "
+    set_error("tcgen05 scoring needs d % 64 == 0, k <= 32 and the user tile + 2 item stages to fit in 227 KB "
               "(d<=256 for bf16, d<=128 for bf16x3); use LGX_SCORE_FP32 otherwise");
     return LGX_ERR_INVALID;
   }
@@ -487,13 +512,20 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   p.mask = make_mask(g); p.users = users;
   p.ws_val = reinterpret_cast<float*>(workspace);
   p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
-  static size_t configured = 0;
-  if (cfg.smem > configured) {
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    configured = cfg.smem;
+  static bool configured = false;
+  if (!configured) {
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    configured = true;
   }
   dim3 grid(plan.n_user_tiles, plan.n_splits);
-  k_score_topk_tc<<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  const bool smallq = cfg.q_cap < 40;
+  if (K <= 24 && !smallq) k_score_topk_tc<24, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  else if (K <= 24) k_score_topk_tc<24, true><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  else if (!smallq) k_score_topk_tc<32, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  else k_score_topk_tc<32, true><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
   LGX_CHECK_LAUNCH();
   return launch_merge_i32(p.ws_val, p.ws_idx, plan.n_splits, B, K, item_offset, M, p.mask, users, out_idx, out_val, st);
 }
