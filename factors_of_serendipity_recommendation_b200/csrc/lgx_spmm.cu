@@ -166,6 +166,109 @@ k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, co
   }
 }
 
+// Specialised kernel for d == 4*G*V (16/32/64/128/256): the row stride is a compile-time constant and rows are
+// indexed with 32-bit float4 offsets (one IMAD.WIDE per gather instead of a 64-bit multiply chain),
+// and steps in which every group of the warp has a full batch of G non-zeros run without any
+// predication.  (ncu on the generic kernel: 38 warp instructions per non-zero step, 64% issue-active
+// -- the gather loop was instruction-bound, not memory-bound.)
+template <int G, int V, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
+             const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
+             float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div) {
+  constexpr int D4 = G * V;            // float4 per embedding row
+  constexpr int D = 4 * D4;
+  constexpr int UU = U > G ? G : U;
+  const int lig = threadIdx.x & (G - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int64_t n_rounds = (n_work + n_groups - 1) / n_groups;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X) + lig;
+
+  for (int64_t round = 0; round < n_rounds; ++round) {
+    const int64_t item = round * n_groups + group;
+    const int32_t* ci = indices;
+    const float* cv = values;
+    int32_t row = 0, len = 0, part = -1;
+    const bool have = item < n_work;
+    if (have) {
+      const int4 w0 = __ldg(reinterpret_cast<const int4*>(work + item));        // start (lo, hi), row, len
+      const int64_t start = ((int64_t)(uint32_t)w0.x) | ((int64_t)w0.y << 32);
+      ci += start; cv += start;
+      row = w0.z; len = w0.w;
+      part = item < n_partials ? (int32_t)item : -1;
+    }
+    int maxlen = len;
+#pragma unroll
+    for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int32_t c_nxt = 0;
+    float a_nxt = 0.f;
+    if (lig < len) { c_nxt = ld_stream_i32(ci + lig); a_nxt = ld_stream_f32(cv + lig); }
+    for (int base = 0; base < maxlen; base += G) {
+      const int32_t c = c_nxt;
+      const float a = a_nxt;
+      const int kn = base + G + lig;
+      c_nxt = 0; a_nxt = 0.f;
+      if (kn < len) { c_nxt = ld_stream_i32(ci + kn); a_nxt = ld_stream_f32(cv + kn); }
+      const int cnt = len - base;
+      if (__all_sync(0xffffffffu, cnt >= G)) {
+        // ---- full batch in every group of the warp: no predicates
+#pragma unroll
+        for (int j0 = 0; j0 < G; j0 += UU) {
+          float4 x[UU][V];
+          float av[UU];
+#pragma unroll
+          for (int j = 0; j < UU; ++j) {
+            const uint32_t cj = (uint32_t)__shfl_sync(0xffffffffu, c, j0 + j, G);
+            av[j] = __shfl_sync(0xffffffffu, a, j0 + j, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[j][v] = __ldg(X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G)));
+          }
+#pragma unroll
+          for (int j = 0; j < UU; ++j)
+#pragma unroll
+            for (int v = 0; v < V; ++v) fma4(acc[v], av[j], x[j][v]);
+        }
+      } else {
+        // ---- ragged tail: a = 0 and column = 0 beyond the row's end (lanes loaded zeros above)
+#pragma unroll
+        for (int j0 = 0; j0 < G; j0 += UU) {
+          if (__all_sync(0xffffffffu, cnt <= j0)) break;
+          float4 x[UU][V];
+          float av[UU];
+#pragma unroll
+          for (int j = 0; j < UU; ++j) {
+            const uint32_t cj = (uint32_t)__shfl_sync(0xffffffffu, c, j0 + j, G);
+            av[j] = __shfl_sync(0xffffffffu, a, j0 + j, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              x[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (j0 + j < cnt) x[j][v] = __ldg(X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G)));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < UU; ++j)
+#pragma unroll
+            for (int v = 0; v < V; ++v) fma4(acc[v], av[j], x[j][v]);
+        }
+      }
+    }
+    if (have) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int col = (lig + v * G) << 2;
+        if (part >= 0) *reinterpret_cast<float4*>(partial + (int64_t)part * D + col) = acc[v];
+        else epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
+      }
+    }
+  }
+}
+
 // d not a multiple of 4: scalar lanes (rare; the reference allows any --recdim).
 __global__ void __launch_bounds__(256)
 k_spmm_scalar(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
@@ -271,6 +374,18 @@ static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, f
                                                            X, S_in, Y, S_out, partial, div, d, g->dinv, hot_rsqrt);
 }
 
+template <int G, int V, int U, int MINB>
+static void launch_fixed(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
+                         float div, cudaStream_t st) {
+  static int max_blocks = 0;
+  if (max_blocks == 0) max_blocks = blocks_for(k_spmm_fixed<G, V, U, MINB>, 256);
+  const int64_t groups_per_block = 256 / G;
+  const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
+  k_spmm_fixed<G, V, U, MINB><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in,
+                                                     Y, S_out, partial, div);
+}
+
 static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div,
                      int32_t d, void* workspace, cudaStream_t st) {
   float* partial = reinterpret_cast<float*>(workspace);
@@ -280,19 +395,27 @@ static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, floa
       const int64_t need = (g->n_work + 7) / 8;
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
       k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d);
+    } else if (tuning().variant == 0 && (d == 16 || d == 32 || d == 64 || d == 128 || d == 256) &&
+               g->n_cols * (int64_t)(d / 4) < ((int64_t)1 << 32)) {
+      // default: compile-time row stride, 4 gathers in flight per lane, >= 4 CTAs per SM
+      // (B200 sweep over U x occupancy at Amazon-Book shape: profiles/r1_spmm_sweep.txt)
+      if (d == 64) launch_fixed<16, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
+      else if (d == 128) launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
+      else if (d == 256) launch_fixed<32, 2, 4, 3>(g, X, S_in, Y, S_out, partial, div, st);
+      else if (d == 32) launch_fixed<8, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
+      else launch_fixed<4, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
     } else if (d == 64) {
-      switch (tuning().variant) {
+      switch (tuning().variant) {   // experiment knob LGX_SPMM_VARIANT (scripts/spmm_sweep.py); 0 = default above
         case 1: launch_spmm<16, 1, true, 8, 3, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
         case 3: launch_spmm<16, 1, true, 16, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 4: launch_spmm<16, 1, true, 8, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
         case 5: if (hot_ok) { launch_spmm<16, 1, true, 8, 2, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
         case 6: if (hot_ok) { launch_spmm<16, 1, true, 8, 3, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
         case 7: if (hot_ok) { launch_spmm<16, 1, true, 4, 4, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
-        case 8: launch_spmm<16, 1, true, 4, 5, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 9: launch_spmm<16, 1, true, 2, 6, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 10: launch_spmm<16, 1, true, 4, 6, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 11: launch_spmm<16, 1, true, 2, 8, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
         case 12: launch_spmm<16, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 20: launch_fixed<16, 1, 8, 2>(g, X, S_in, Y, S_out, partial, div, st); break;
+        case 21: launch_fixed<16, 1, 8, 3>(g, X, S_in, Y, S_out, partial, div, st); break;
+        case 24: launch_fixed<16, 1, 8, 4>(g, X, S_in, Y, S_out, partial, div, st); break;
+        case 26: launch_fixed<16, 1, 4, 5>(g, X, S_in, Y, S_out, partial, div, st); break;
         default: launch_spmm<16, 1, true, 4, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
       }
     } else if (d == 128) {
