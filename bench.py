@@ -178,25 +178,42 @@ def run_ours(args, shape):
     mode = args.mode
     mode_id = _lgx.MODES[mode]
 
-    u, i = synth.make_interactions(nu, mi, E, seed=2020)
-    ue, ie = synth.make_embeddings(nu, mi, d, seed=2020)
+    big = E > 20_000_000                      # generated on the device, never visits the host
+    huge = E >= 500_000_000                   # tables of several GB: no host copies, no e2e leg
     cfg = dict(world.config)
-    cfg.update(pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy(), lightGCN_n_layers=N_LAYERS, latent_dim_rec=d,
-               score_mode=mode)
-    ds = dataloader.InteractionDataset(nu, mi, u, i, device=dev)
-    m = model.LightGCN(cfg, ds).to(dev).eval()
+    cfg.update(lightGCN_n_layers=N_LAYERS, latent_dim_rec=d, score_mode=mode)
+    if big:
+        u_d, i_d = synth.make_interactions_device(nu, mi, E, seed=2020, device=dev)
+        g = _lgx.Graph.build(nu, mi, u_d, i_d, chunk_nnz=args.chunk)
+        del u_d, i_d
+        torch.cuda.empty_cache()
+        ds = dataloader.InteractionDataset(nu, mi, None, None, device=dev, graph=g, train_size=E)
+        u = i = None
+    else:
+        u, i = synth.make_interactions(nu, mi, E, seed=2020)
+        ds = dataloader.InteractionDataset(nu, mi, u, i, device=dev)
+    if huge:
+        m, ue, ie = None, None, None
+        gen = torch.Generator(device=dev).manual_seed(2020)
+        E0_huge = torch.empty(nu + mi, d, device=dev).normal_(std=0.1, generator=gen)     # PT/model.py:112-113
+    else:
+        ue, ie = synth.make_embeddings(nu, mi, d, seed=2020)
+        cfg.update(pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy())
+        m = model.LightGCN(cfg, ds).to(dev).eval()
     g = ds.getGraphHandle()
     N, nnz = g.n_rows, g.nnz
-    all_users = torch.arange(nu, dtype=torch.int64, device=dev)
+    n_score = nu if nu <= 200_000 else 65_536      # huge graphs: score a 65 536-user batch per step (configs[4] style)
+    all_users = torch.arange(n_score, dtype=torch.int64, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     if world_size > 1:
         from factors_of_serendipity_recommendation_b200 import parallel
         engine = parallel.ShardedEngine(g, nu, mi, d, N_LAYERS, rank, world_size, dev)
+        torch.cuda.empty_cache()
     else:
         engine = None
 
-    E0 = m._flat_if_fused()
+    E0 = E0_huge if huge else m._flat_if_fused()
     assert E0 is not None
     light = torch.empty_like(E0)
 
@@ -207,10 +224,10 @@ def run_ours(args, shape):
         g.propagate_fwd(E0, N_LAYERS, out=light)
         au, ai = light[:nu], light[nu:]
         if mode_id == _lgx.SCORE_FP32:
-            U_op, I_op = au, ai
+            U_op, I_op = au[:n_score], ai
         else:
             I_op = _lgx.pack_operand(ai, None, mode_id, True)
-            U_op = _lgx.pack_operand(au, None, mode_id, False)
+            U_op = _lgx.pack_operand(au, all_users, mode_id, False)
         return _lgx.score_topk(g, U_op, all_users, I_op, d, K_TOP, mode_id)
 
     def timed_step():
@@ -226,10 +243,10 @@ def run_ours(args, shape):
         ev[1].record()
         au, ai = light[:nu], light[nu:]
         if mode_id == _lgx.SCORE_FP32:
-            U_op, I_op = au, ai
+            U_op, I_op = au[:n_score], ai
         else:
             I_op = _lgx.pack_operand(ai, None, mode_id, True)
-            U_op = _lgx.pack_operand(au, None, mode_id, False)
+            U_op = _lgx.pack_operand(au, all_users, mode_id, False)
         ev[2].record()
         _lgx.score_topk(g, U_op, all_users, I_op, d, K_TOP, mode_id)
         ev[3].record()
@@ -261,45 +278,46 @@ def run_ours(args, shape):
     else:
         t_prop_mean, t_pack_mean, t_score_mean = (statistics.mean(x) for x in (t_prop, t_pack, t_score))
     ms_per_step = total_ms / args.steps
-    value = nu / (ms_per_step * 1e-3)
+    value = n_score / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (H2D of the tables, D2H of the top-20)
-    host_u, host_i = ue.clone().pin_memory(), ie.clone().pin_memory()
-    host_out = torch.empty(nu, K_TOP, dtype=torch.int64).pin_memory()
-    e2e_ms = []
+    e2e_total = None
+    if not huge:
+        host_u, host_i = ue.clone().pin_memory(), ie.clone().pin_memory()
+        host_out = torch.empty(n_score, K_TOP, dtype=torch.int64).pin_memory()
 
-    def e2e_step():
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        m.embedding_user.weight.data.copy_(host_u, non_blocking=True)
-        m.embedding_item.weight.data.copy_(host_i, non_blocking=True)
-        m._eval_cache = None
-        if engine is not None:
-            idx, _ = engine.step(m._flat_if_fused(), all_users, K_TOP, mode_id, shard=args.shard)
-        else:
-            idx, _ = m.topk(all_users, K_TOP, mode=mode)      # the call a user makes (computer() inside)
-        host_out.copy_(idx, non_blocking=True)
-        b.record()
-        return a, b
+        def e2e_step():
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            m.embedding_user.weight.data.copy_(host_u, non_blocking=True)
+            m.embedding_item.weight.data.copy_(host_i, non_blocking=True)
+            m._eval_cache = None
+            if engine is not None:
+                idx, _ = engine.step(m._flat_if_fused(), all_users, K_TOP, mode_id, shard=args.shard)
+            else:
+                idx, _ = m.topk(all_users, K_TOP, mode=mode)      # the call a user makes (computer() inside)
+            host_out.copy_(idx, non_blocking=True)
+            b.record()
+            return a, b
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    pairs = [e2e_step() for _ in range(args.steps)]
-    barrier()
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        pairs = [e2e_step() for _ in range(args.steps)]
+        barrier()
+        e2e_total = sum(a.elapsed_time(b) for a, b in pairs)
+        if world_size > 1:
+            tt = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_total = tt.item()
     clocks = sampler.stop() if rank == 0 else None
-    e2e_total = sum(a.elapsed_time(b) for a, b in pairs)
-    if world_size > 1:
-        tt = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_total = tt.item()
-    e2e_value = nu / (e2e_total / args.steps * 1e-3)
+    e2e_value = n_score / (e2e_total / args.steps * 1e-3) if e2e_total else None
 
     if rank == 0:
         layer_bytes, fwd_bytes = spmm_algorithmic_bytes(N, nnz, d, N_LAYERS)
         spmm_gbs = fwd_bytes / (t_prop_mean * 1e-3) / 1e9
-        flops = 2.0 * nu * mi * d
+        flops = 2.0 * n_score * mi * d
         score_tf = flops / (t_score_mean * 1e-3) / 1e12
         roof_spmm = {"bound": "hbm", "achieved": spmm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": spmm_gbs / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
@@ -319,20 +337,21 @@ def run_ours(args, shape):
             "dtype": "f32 propagation, " + {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (hi/lo split)"}[mode] + " scoring",
             "data": "synthetic",
             "config": {"workload": args.workload, "n_users": nu, "m_items": mi, "edges": E, "nnz": nnz, "d": d,
-                       "layers": N_LAYERS, "k": K_TOP, "score_mode": mode, "l2": "flushed between steps (512 MB fill)",
+                       "layers": N_LAYERS, "k": K_TOP, "users_scored_per_step": n_score, "score_mode": mode, "l2": "flushed between steps (512 MB fill)",
                        "parallelism": "1 GPU" if world_size == 1 else
                        f"row-sharded SpMM + NCCL all-gather per layer, scoring sharded by {args.shard} x{world_size}"},
             "spmm": {"propagated_edges_per_s": N_LAYERS * nnz / (t_prop_mean * 1e-3), "hbm_gbs": spmm_gbs,
                      "ms": t_prop_mean, "layers": N_LAYERS},
-            "scoring": {"users_per_s": nu / (t_score_mean * 1e-3), "tflops": score_tf, "ms": t_score_mean,
+            "scoring": {"users_per_s": n_score / (t_score_mean * 1e-3), "tflops": score_tf, "ms": t_score_mean,
                         "pack_ms": t_pack_mean},
             "roofline": dominant, "roofline_spmm": roof_spmm, "roofline_scoring": roof_score,
             "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": int((nu + mi) * d * 4),
-                    "d2h_bytes_per_step": int(nu * K_TOP * 8), "ms_per_step": e2e_total / args.steps},
+                    "d2h_bytes_per_step": int(n_score * K_TOP * 8),
+                    "ms_per_step": e2e_total / args.steps if e2e_total else None},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
-        if world_size == 1 and not args.no_cpu:
+        if world_size == 1 and not args.no_cpu and not big:
             line["cpu_baseline"] = cpu_baseline_sample(shape, u, i, ue, ie)
         print(json.dumps(line), flush=True)
     if world_size > 1:
@@ -348,6 +367,7 @@ def main():
     ap.add_argument("--workload", default="amazon-book")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chunk", type=int, default=0, help="long-row split size for the graph build (0 = default 256)")
     ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"], help="scoring split at N > 1")
     args = ap.parse_args()
     from factors_of_serendipity_recommendation_b200 import synth

@@ -10,7 +10,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "liblgx.so")
+LIB_PATH = os.environ.get("LGX_LIB_PATH", os.path.join(_PKG, "liblgx.so"))   # override: A/B builds in experiments
 
 SCORE_FP32, SCORE_BF16, SCORE_BF16X3 = 0, 1, 2
 MODES = {"fp32": SCORE_FP32, "bf16": SCORE_BF16, "bf16x3": SCORE_BF16X3}

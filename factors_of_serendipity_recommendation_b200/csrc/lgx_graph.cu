@@ -270,7 +270,7 @@ int lgx_graph_build(int32_t n_users, int32_t m_items, int64_t n_edges, const int
   LGX_CHECK_DEVICE();
   LGX_REQUIRE(out != nullptr, "out is NULL");
   LGX_REQUIRE(n_users > 0 && m_items > 0, "n_users and m_items must be positive");
-  LGX_REQUIRE(n_edges >= 0 && n_edges <= (int64_t)1 << 30, "n_edges out of range (max 2^30 interactions per handle)");
+  LGX_REQUIRE(n_edges >= 0 && n_edges <= 1073000000, "n_edges out of range (max 1.073e9 interactions per handle: 2E must fit int32 for the run-length pass)");
   LGX_REQUIRE(n_edges == 0 || (users && items), "users/items NULL");
   LGX_REQUIRE((int64_t)n_users + m_items < ((int64_t)1 << 31), "n_users + m_items must fit int32");
   cudaStream_t st = (cudaStream_t)stream;

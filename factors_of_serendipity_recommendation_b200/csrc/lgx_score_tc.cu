@@ -184,7 +184,15 @@ struct EpiState {
   int32_t li[KMAX];
   int qn;                       // pending candidates in the queue
   float* qval; int32_t* qidx;   // queue, column layout [q_cap][256]
+  float* thr_mine;              // shared memory: largest float below my K-th best (published at every flush)
+  const float* thr_other;       // the same from the thread that owns the other column half of this row
   __device__ __forceinline__ float thresh() const { return lv[KMAX - 1]; }
+  // Filter threshold: a score must beat my own K-th best, and must be >= the partner's K-th best -- the
+  // partner already holds K items of this row at least that good, so anything below it cannot reach the
+  // row's final top-K (equal scores are kept: the final merge breaks ties by item id).
+  __device__ __forceinline__ float filter() const {
+    return fmaxf(lv[KMAX - 1], *reinterpret_cast<const volatile float*>(thr_other));
+  }
   __device__ __forceinline__ void init(int K) {
 #pragma unroll
     for (int p = 0; p < KMAX; ++p) {
@@ -206,8 +214,11 @@ struct EpiState {
     li[0] = g0 ? xi : li[0];
   }
   __device__ __forceinline__ void flush() {
-    for (int q = 0; q < qn; ++q) insert(qval[q * TC_EPI_THREADS], qidx[q * TC_EPI_THREADS]);
+    for (int q = 0; q < qn; q += TC_EPI_THREADS) insert(qval[q], qidx[q]);
     qn = 0;
+    const float t = lv[KMAX - 1];                       // publish prev_float(K-th best); -inf stays -inf
+    const int tb = __float_as_int(t);
+    *thr_mine = (t == -CUDART_INF_F || t != t) ? -CUDART_INF_F : __int_as_float(tb > 0 ? tb - 1 : (tb == 0 ? (int)0x80000001 : tb + 1));
     __syncwarp();
   }
 };
@@ -219,6 +230,30 @@ struct EpiState {
 template <int KMAX, bool SMALLQ>
 __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KMAX>& st, int M, int q_cap,
                                           TrainCursor& tc) {
+  // Train items of this row inside the chunk (rare per lane, ~2%): overwrite their score with -inf.
+#ifndef LGX_EXCL_SWITCH
+#define LGX_EXCL_SWITCH 0   // A/B on B200: jump table 2.65 ms vs predicated sweep 2.38 ms (fewer instructions, but BRX divergence costs more)
+#endif
+#if LGX_EXCL_SWITCH
+  // One jump-table store per excluded column (fewer instructions than the predicated sweep, which
+  // runs whenever ANY lane of the warp has a train item in the chunk: 47% of chunks at Amazon-Book shape).
+  while (tc.next < j0 + 32) {
+    if (tc.next >= j0) {
+      switch (tc.next - j0) {
+#define LGX_EXCL_CASE(i) case i: v[i] = 0xff800000u; break;
+        LGX_EXCL_CASE(0) LGX_EXCL_CASE(1) LGX_EXCL_CASE(2) LGX_EXCL_CASE(3) LGX_EXCL_CASE(4) LGX_EXCL_CASE(5)
+        LGX_EXCL_CASE(6) LGX_EXCL_CASE(7) LGX_EXCL_CASE(8) LGX_EXCL_CASE(9) LGX_EXCL_CASE(10) LGX_EXCL_CASE(11)
+        LGX_EXCL_CASE(12) LGX_EXCL_CASE(13) LGX_EXCL_CASE(14) LGX_EXCL_CASE(15) LGX_EXCL_CASE(16) LGX_EXCL_CASE(17)
+        LGX_EXCL_CASE(18) LGX_EXCL_CASE(19) LGX_EXCL_CASE(20) LGX_EXCL_CASE(21) LGX_EXCL_CASE(22) LGX_EXCL_CASE(23)
+        LGX_EXCL_CASE(24) LGX_EXCL_CASE(25) LGX_EXCL_CASE(26) LGX_EXCL_CASE(27) LGX_EXCL_CASE(28) LGX_EXCL_CASE(29)
+        LGX_EXCL_CASE(30) LGX_EXCL_CASE(31)
+#undef LGX_EXCL_CASE
+      }
+    }
+    tc.advance();
+  }
+  __syncwarp();
+#else
   if (tc.next < j0 + 32) {
     uint32_t excl = 0;
     do {
@@ -231,6 +266,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KM
         if ((excl >> i) & 1u) v[i] = 0xff800000u;   // -inf
     }
   }
+#endif
   float gm[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -239,7 +275,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KM
     gm[g] = fmaxf(max3(a, b, __uint_as_float(v[8 * g + 6])), __uint_as_float(v[8 * g + 7]));
   }
   const float m = fmaxf(max3(gm[0], gm[1], gm[2]), gm[3]);
-  const float th = st.thresh();
+  const float th = st.filter();
   if (__any_sync(0xffffffffu, m > th)) {               // warp-uniform
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -249,20 +285,20 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KM
           const float s = __uint_as_float(v[i]);
           const int j = j0 + i;
           if (s > th && j < M) {
-            st.qval[st.qn * TC_EPI_THREADS] = s;
-            st.qidx[st.qn * TC_EPI_THREADS] = j;
-            ++st.qn;
+            st.qval[st.qn] = s;               // qn counts in units of one queue row (256 entries)
+            st.qidx[st.qn] = j;
+            st.qn += TC_EPI_THREADS;
           }
         }
       }
       if (SMALLQ) {                                     // small queues (big user tile in smem): check per group
         __syncwarp();
-        if (__any_sync(0xffffffffu, st.qn > q_cap - 8)) st.flush();
+        if (__any_sync(0xffffffffu, st.qn > (q_cap - 8) * TC_EPI_THREADS)) st.flush();
       }
     }
     if (!SMALLQ) {
       __syncwarp();
-      if (__any_sync(0xffffffffu, st.qn > q_cap - 32)) st.flush();   // warp-convergent
+      if (__any_sync(0xffffffffu, st.qn > (q_cap - 32) * TC_EPI_THREADS)) st.flush();   // warp-convergent
     }
   }
 }
@@ -291,6 +327,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   const uint32_t bar_tfull = bar_a + 8;                         // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5));
+  float* thr_all = reinterpret_cast<float*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5) + 16);   // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u_tile = blockIdx.x, split = blockIdx.y;
@@ -319,6 +356,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (threadIdx.x < TC_EPI_THREADS) thr_all[threadIdx.x] = -CUDART_INF_F;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -378,6 +416,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     EpiState<KMAX> st;
     st.init(p.K);
     st.qval = qval_all + col; st.qidx = qidx_all + col;
+    st.thr_mine = thr_all + col; st.thr_other = thr_all + (col ^ TC_TILE_U);   // partner: same row, other half
     const int u = u_tile * TC_TILE_U + row;
     const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
     TrainCursor tcur;
@@ -478,7 +517,7 @@ static TcConfig tc_config(int d, int K, int mode) {
   size_t fixed = 0;
   for (c.q_cap = 40; c.q_cap >= 16; c.q_cap -= 24) {    // shrink the candidate queues before giving up stages
     fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)c.q_cap * TC_EPI_THREADS * 8 +
-            8 * (2 * TC_MAX_STAGES + 5) + 16;
+            8 * (2 * TC_MAX_STAGES + 5) + 16 + 4 * TC_EPI_THREADS;
     if (fixed + 3 * (size_t)TC_B_STAGE_BYTES <= TC_SMEM_LIMIT) break;
   }
   if (c.q_cap < 16) c.q_cap = 16;
@@ -514,6 +553,7 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
   static bool configured = false;
   if (!configured) {
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
@@ -522,7 +562,8 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   }
   dim3 grid(plan.n_user_tiles, plan.n_splits);
   const bool smallq = cfg.q_cap < 40;
-  if (K <= 24 && !smallq) k_score_topk_tc<24, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  if (K <= 20 && !smallq) k_score_topk_tc<20, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);   // the reference's default topks=[20]
+  else if (K <= 24 && !smallq) k_score_topk_tc<24, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
   else if (K <= 24) k_score_topk_tc<24, true><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
   else if (!smallq) k_score_topk_tc<32, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
   else k_score_topk_tc<32, true><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);

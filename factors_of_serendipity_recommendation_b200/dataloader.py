@@ -76,17 +76,19 @@ class InteractionDataset(BasicDataset):
     """A dataset from in-memory interaction arrays (synthetic graphs, tests, bench)."""
 
     def __init__(self, n_users: int, m_items: int, train_user, train_item, test_dict=None, config=None,
-                 device=None, path=None):
+                 device=None, path=None, graph=None, train_size=None):
+        """``graph``: a prebuilt _lgx.Graph (graphs generated on the device never visit the host; then
+        train_user / train_item may be None and train_size gives trainDataSize)."""
         self.config = world.config if config is None else config
         self.device = torch.device(device) if device is not None else world.device
         self.n_user, self.m_item = int(n_users), int(m_items)
-        self.trainUser = np.asarray(train_user)
-        self.trainItem = np.asarray(train_item)
-        self.traindataSize = int(self.trainUser.size)
+        self.trainUser = np.asarray(train_user) if train_user is not None else None
+        self.trainItem = np.asarray(train_item) if train_item is not None else None
+        self.traindataSize = int(train_size if train_size is not None else self.trainUser.size)
         self.__testDict = dict(test_dict) if test_dict is not None else {}
         self.path = path
         self.Graph = None
-        self._graph = None
+        self._graph = graph
         self._allPos = None
         self._csr_host = None
 

@@ -17,6 +17,8 @@ SHAPES = {
     "gowalla": (29_858, 40_981, 1_027_370, 64),
     "yelp2018": (31_668, 38_048, 1_561_406, 64),
     "amazon-book": (52_643, 91_599, 2_984_108, 64),
+    "synth-10m": (100_000, 20_000, 10_000_000, 128),
+    "synth-100m": (1_000_000, 200_000, 100_000_000, 128),
     "synth-1b": (10_000_000, 2_000_000, 1_000_000_000, 128),
 }
 
@@ -60,6 +62,45 @@ def make_interactions(n_users: int, m_items: int, n_edges: int, seed: int = 2020
     users = (keys // m_items).astype(np.int32)
     items = (keys % m_items).astype(np.int32)
     return users, items
+
+
+def make_interactions_device(n_users: int, m_items: int, n_edges: int, seed: int = 2020, device="cuda"):
+    """Same distributional contract as make_interactions (unique pairs, every user and item covered,
+    item popularity ~ rank^-0.8, user activity ~ log-normal(1)), generated with torch ops on the GPU for
+    the shapes numpy cannot build in reasonable time (>= 10^7 edges).  Deterministic per (seed, shape).
+    Returns int32 device tensors sorted by (user, item)."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    pop = torch.arange(1, m_items + 1, device=device, dtype=torch.float64) ** -0.8
+    pop = pop[torch.randperm(m_items, device=device, generator=g)]
+    pop_cdf = torch.cumsum(pop / pop.sum(), 0)
+    act = torch.exp(torch.randn(n_users, device=device, generator=g, dtype=torch.float64))
+    act_cdf = torch.cumsum(act / act.sum(), 0)
+
+    def draw(cdf, k, hi):
+        r = torch.rand(k, device=device, generator=g, dtype=torch.float64)
+        return torch.searchsorted(cdf, r).clamp_(max=hi - 1)
+
+    cov = torch.cat([torch.arange(n_users, device=device) * m_items + draw(pop_cdf, n_users, m_items),
+                     draw(act_cdf, m_items, n_users) * m_items + torch.arange(m_items, device=device)])
+    keys = torch.unique(cov)
+    n_cov_unique = keys.numel()
+    is_cov_sorted = None
+    while keys.numel() < n_edges:
+        need = n_edges - keys.numel()
+        k = int(need * 1.25) + 4096
+        extra = draw(act_cdf, k, n_users) * m_items + draw(pop_cdf, k, m_items)
+        keys = torch.unique(torch.cat([keys, extra]))
+    if keys.numel() > n_edges:
+        cov_u = torch.unique(cov)
+        pos = torch.searchsorted(cov_u, keys).clamp_(max=cov_u.numel() - 1)
+        removable = torch.nonzero(cov_u[pos] != keys).squeeze(1)
+        drop = removable[torch.randperm(removable.numel(), device=device, generator=g)[: keys.numel() - n_edges]]
+        keep = torch.ones(keys.numel(), dtype=torch.bool, device=device)
+        keep[drop] = False
+        keys = keys[keep]
+    return (keys // m_items).to(torch.int32), (keys % m_items).to(torch.int32)
 
 
 def make_embeddings(n_users: int, m_items: int, dim: int, seed: int = 2020, trained_like: bool = False):

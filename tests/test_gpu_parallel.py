@@ -52,7 +52,7 @@ def _worker(rank, world, port, out_dir):
 @pytest.mark.timeout(600)
 def test_sharded_engine_matches_single_gpu(tmp_path):
     import torch.multiprocessing as mp
-    world = min(2, torch.cuda.device_count())
+    world = min(8, torch.cuda.device_count())
     port = 29600 + (os.getpid() % 2000)
     mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
