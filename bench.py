@@ -208,7 +208,7 @@ def run_ours(args, shape):
 
     if world_size > 1:
         from factors_of_serendipity_recommendation_b200 import parallel
-        engine = parallel.ShardedEngine(g, nu, mi, d, N_LAYERS, rank, world_size, dev)
+        engine = parallel.ShardedEngine(g, nu, mi, d, N_LAYERS, rank, world_size, dev, propagate=args.propagate)
         torch.cuda.empty_cache()
     else:
         engine = None
@@ -339,7 +339,8 @@ def run_ours(args, shape):
             "config": {"workload": args.workload, "n_users": nu, "m_items": mi, "edges": E, "nnz": nnz, "d": d,
                        "layers": N_LAYERS, "k": K_TOP, "users_scored_per_step": n_score, "score_mode": mode, "l2": "flushed between steps (512 MB fill)",
                        "parallelism": "1 GPU" if world_size == 1 else
-                       f"row-sharded SpMM + NCCL all-gather per layer, scoring sharded by {args.shard} x{world_size}"},
+                       f"propagation {engine.mode} (fused = SpMM epilogue stores into peer memory over NVLink; allgather = NCCL per layer), "
+                       f"scoring sharded by {args.shard} x{world_size}"},
             "spmm": {"propagated_edges_per_s": N_LAYERS * nnz / (t_prop_mean * 1e-3), "hbm_gbs": spmm_gbs,
                      "ms": t_prop_mean, "layers": N_LAYERS},
             "scoring": {"users_per_s": n_score / (t_score_mean * 1e-3), "tflops": score_tf, "ms": t_score_mean,
@@ -355,6 +356,7 @@ def run_ours(args, shape):
             line["cpu_baseline"] = cpu_baseline_sample(shape, u, i, ue, ie)
         print(json.dumps(line), flush=True)
     if world_size > 1:
+        engine.close()
         dist.destroy_process_group()
 
 
@@ -367,6 +369,8 @@ def main():
     ap.add_argument("--workload", default="amazon-book")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--propagate", default="auto", choices=["auto", "fused", "allgather", "replicated"],
+                    help="propagation exchange at N > 1 (parallel.ShardedEngine)")
     ap.add_argument("--chunk", type=int, default=0, help="long-row split size for the graph build (0 = default 256)")
     ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"], help="scoring split at N > 1")
     args = ap.parse_args()

@@ -32,6 +32,11 @@ _SIGS = {
     "lgx_graph_destroy": (C.c_int, [_P]),
     "lgx_spmm_workspace_bytes": (C.c_size_t, [_P, C.c_int32]),
     "lgx_spmm": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_int32, _P, _P]),
+    "lgx_spmm_peers": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.c_int32, C.c_int64, C.c_int32, _P, C.c_float, C.c_int32, _P, _P]),
+    "lgx_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P), C.c_char_p]),
+    "lgx_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "lgx_peer_close": (C.c_int, [_P]),
+    "lgx_peer_free": (C.c_int, [_P]),
     "lgx_propagate_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "lgx_propagate_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "lgx_propagate_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
@@ -188,6 +193,16 @@ class Graph:
         with torch.cuda.device(self.device):
             check(lib().lgx_spmm(self.handle, ptr(X), ptr(S_in), ptr(Y), ptr(S_out), div, d, ptr(ws), stream()))
 
+    def spmm_peers(self, X, peer_ptrs, row_offset: int, S_in=None, S_out=None, div: float = 1.0, store_mean: bool = False):
+        """One layer whose output rows go straight into every rank's gathered buffer (peer_ptrs: list of ints)."""
+        require_cuda(X, S_in, S_out)
+        d = X.shape[1]
+        ws = self.workspace(lib().lgx_spmm_workspace_bytes(self.handle, d), ("spmm", d))
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        with torch.cuda.device(self.device):
+            check(lib().lgx_spmm_peers(self.handle, ptr(X), ptr(S_in), arr, len(peer_ptrs), row_offset, int(store_mean),
+                                       ptr(S_out), div, d, ptr(ws), stream()))
+
     def propagate_fwd(self, E0: torch.Tensor, n_layers: int, out=None, layers_out=None) -> torch.Tensor:
         require_cuda(E0, out, layers_out)
         if E0.dtype != torch.float32 or E0.shape[0] != self.n_rows:
@@ -217,6 +232,45 @@ class Graph:
         with torch.cuda.device(self.device):
             check(lib().lgx_sample_bpr(self.handle, n_samples, per_user, seed, ptr(out), stream()))
         return out
+
+
+class PeerBuffer:
+    """A device buffer the other ranks of the node can map (CUDA IPC): backs the gathered layers of the
+    fused SpMM + all-gather.  ``tensor`` is a zero-copy torch view of the local allocation."""
+
+    class _CAI:
+        def __init__(self, p, shape):
+            self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (p, False), "version": 3,
+                                             "strides": None}
+
+    def __init__(self, shape, device):
+        self.shape, self.device = tuple(shape), device
+        nbytes = 4
+        for x in self.shape:
+            nbytes *= int(x)
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            check(lib().lgx_peer_alloc(nbytes, C.byref(p), h))
+        self.ptr, self.handle = int(p.value), h.raw
+        self.tensor = torch.as_tensor(PeerBuffer._CAI(self.ptr, self.shape), device=device)
+        self.opened = []
+
+    def open_peer(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().lgx_peer_open(handle, C.byref(p)))
+        self.opened.append(int(p.value))
+        return int(p.value)
+
+    def close(self):
+        for p in self.opened:
+            lib().lgx_peer_close(C.c_void_p(p))
+        self.opened = []
+        if self.ptr:
+            self.tensor = None
+            lib().lgx_peer_free(C.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 # ------------------------------------------------------------------------------------- free functions

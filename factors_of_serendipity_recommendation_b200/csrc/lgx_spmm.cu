@@ -13,6 +13,7 @@
 // in a fixed order (deterministic, no float atomics).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "lgx_common.cuh"
 
@@ -37,18 +38,36 @@ __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
   a.w = fmaf(v, x.w, a.w);
 }
 
+// Fused all-gather: the epilogue may also store the row into every rank's copy of the gathered layer
+// (peer device pointers mapped through CUDA IPC; NVLink P2P stores).  value = acc (next layer's input)
+// or the finished running mean (last layer).
+constexpr int kMaxPeers = 16;
+struct PeerOut {
+  float* ptr[kMaxPeers];
+  int n;                 // 0 = no peer output
+  int store_mean;        // 0: store acc, 1: store (S_in + acc) / div
+  int64_t row_offset;    // first row of this rank's block inside the gathered layout
+};
+
 // Epilogue shared by the direct path and the long-row reducer.
-__device__ __forceinline__ void epilogue4(float4 acc, int64_t off, const float* S_in,
-                                          float* __restrict__ Y, float* S_out, float div) {
+__device__ __forceinline__ float4 epilogue4(float4 acc, int64_t off, const float* S_in,
+                                            float* __restrict__ Y, float* S_out, float div) {
   if (Y) *reinterpret_cast<float4*>(Y + off) = acc;
+  float4 s = acc;
   if (S_out) {
-    float4 s = *reinterpret_cast<const float4*>(S_in + off);
+    s = *reinterpret_cast<const float4*>(S_in + off);
     s.x += acc.x; s.y += acc.y; s.z += acc.z; s.w += acc.w;
     if (div != 1.0f) {
       s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
     }
     *reinterpret_cast<float4*>(S_out + off) = s;
   }
+  return s;
+}
+__device__ __forceinline__ void peer_store4(const PeerOut& po, int64_t row, int d, int col, float4 acc, float4 mean) {
+  const float4 v = po.store_mean ? mean : acc;
+  const int64_t off = (po.row_offset + row) * d + col;
+  for (int p = 0; p < po.n; ++p) *reinterpret_cast<float4*>(po.ptr[p] + off) = v;
 }
 
 __device__ __forceinline__ float4 ld_gather_f4_keep(const float* p) {   // hot row: keep in L1
@@ -175,7 +194,7 @@ template <int G, int V, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
              const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
-             float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div) {
+             float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, const PeerOut po) {
   constexpr int D4 = G * V;            // float4 per embedding row
   constexpr int D = 4 * D4;
   constexpr int UU = U > G ? G : U;
@@ -262,8 +281,12 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int col = (lig + v * G) << 2;
-        if (part >= 0) *reinterpret_cast<float4*>(partial + (int64_t)part * D + col) = acc[v];
-        else epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
+        if (part >= 0) {
+          *reinterpret_cast<float4*>(partial + (int64_t)part * D + col) = acc[v];
+        } else {
+          const float4 mean = epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
+          if (po.n > 0) peer_store4(po, row, D, col, acc[v], mean);
+        }
       }
     }
   }
@@ -305,7 +328,7 @@ k_spmm_scalar(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_parti
 // then the slices are combined in order through shared memory (deterministic).
 __global__ void __launch_bounds__(256)
 k_spmm_long(const LongRow* __restrict__ long_rows, int64_t n_long, const float* __restrict__ partial,
-            const float* S_in, float* __restrict__ Y, float* S_out, float div, int d) {
+            const float* S_in, float* __restrict__ Y, float* S_out, float div, int d, const PeerOut po) {
   __shared__ float red[256];
   const int colsP = min(d, 256);
   const int slices = 256 / colsP;
@@ -330,9 +353,16 @@ k_spmm_long(const LongRow* __restrict__ long_rows, int64_t n_long, const float* 
         for (int s2 = 1; s2 < slices; ++s2) acc += red[s2 * colsP + cl];
         const int64_t off = (int64_t)r.row * d + c;
         if (Y) Y[off] = acc;
+        float s = acc;
         if (S_out) {
-          float s = S_in[off] + acc;
-          S_out[off] = div != 1.0f ? __fdiv_rn(s, div) : s;
+          s = S_in[off] + acc;
+          s = div != 1.0f ? __fdiv_rn(s, div) : s;
+          S_out[off] = s;
+        }
+        if (po.n > 0) {
+          const float v = po.store_mean ? s : acc;
+          const int64_t poff = (po.row_offset + r.row) * d + c;
+          for (int p = 0; p < po.n; ++p) po.ptr[p][poff] = v;
         }
       }
     }
@@ -376,34 +406,39 @@ static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, f
 
 template <int G, int V, int U, int MINB>
 static void launch_fixed(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
-                         float div, cudaStream_t st) {
+                         float div, cudaStream_t st, const PeerOut& po = PeerOut{}) {
   static int max_blocks = 0;
   if (max_blocks == 0) max_blocks = blocks_for(k_spmm_fixed<G, V, U, MINB>, 256);
   const int64_t groups_per_block = 256 / G;
   const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
   k_spmm_fixed<G, V, U, MINB><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in,
-                                                     Y, S_out, partial, div);
+                                                     Y, S_out, partial, div, po);
 }
 
 static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div,
-                     int32_t d, void* workspace, cudaStream_t st) {
+                     int32_t d, void* workspace, cudaStream_t st, const PeerOut& po = PeerOut{}) {
   float* partial = reinterpret_cast<float*>(workspace);
+  const bool fixed_ok = (d == 16 || d == 32 || d == 64 || d == 128 || d == 256) &&
+                        g->n_cols * (int64_t)(d / 4) < ((int64_t)1 << 32);
+  if (po.n > 0 && !fixed_ok) {
+    set_error("fused peer output needs d in {16,32,64,128,256}");
+    return LGX_ERR_INVALID;
+  }
   if (g->n_work > 0) {
     const bool hot_ok = g->values_are_dinv_products;   // HOT needs value == dinv[row]*dinv[col]
     if (d % 4 != 0) {
       const int64_t need = (g->n_work + 7) / 8;
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
       k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d);
-    } else if (tuning().variant == 0 && (d == 16 || d == 32 || d == 64 || d == 128 || d == 256) &&
-               g->n_cols * (int64_t)(d / 4) < ((int64_t)1 << 32)) {
+    } else if ((tuning().variant == 0 || po.n > 0) && fixed_ok) {
       // default: compile-time row stride, 4 gathers in flight per lane, >= 4 CTAs per SM
       // (B200 sweep over U x occupancy at Amazon-Book shape: profiles/r1_spmm_sweep.txt)
-      if (d == 64) launch_fixed<16, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
-      else if (d == 128) launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
-      else if (d == 256) launch_fixed<32, 2, 4, 3>(g, X, S_in, Y, S_out, partial, div, st);
-      else if (d == 32) launch_fixed<8, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
-      else launch_fixed<4, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st);
+      if (d == 64) launch_fixed<16, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
+      else if (d == 128) launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
+      else if (d == 256) launch_fixed<32, 2, 4, 3>(g, X, S_in, Y, S_out, partial, div, st, po);
+      else if (d == 32) launch_fixed<8, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
+      else launch_fixed<4, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
     } else if (d == 64) {
       switch (tuning().variant) {   // experiment knob LGX_SPMM_VARIANT (scripts/spmm_sweep.py); 0 = default above
         case 1: launch_spmm<16, 1, true, 8, 3, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
@@ -437,7 +472,7 @@ static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, floa
   }
   if (g->n_long > 0) {
     const int blocks = (int)std::min<int64_t>(g->n_long, (int64_t)sm_count() * 8);
-    k_spmm_long<<<blocks, 256, 0, st>>>(g->long_rows, g->n_long, partial, S_in, Y, S_out, div, d);
+    k_spmm_long<<<blocks, 256, 0, st>>>(g->long_rows, g->n_long, partial, S_in, Y, S_out, div, d, po);
     LGX_CHECK_LAUNCH();
   }
   return LGX_OK;
@@ -466,6 +501,62 @@ int lgx_spmm(const lgx_graph* g, const float* X, const float* S_in, float* Y, fl
   LGX_REQUIRE(g->n_partials == 0 || workspace, "graph has split rows: workspace required");
   LGX_REQUIRE(div != 0.0f, "div must be non-zero");
   return spmm_impl(g, X, S_in, Y, S_out, div, d, workspace, (cudaStream_t)stream);
+}
+
+int lgx_spmm_peers(const lgx_graph* g, const float* X, const float* S_in, float* const* peers_host, int32_t n_peers,
+                   int64_t row_offset, int32_t store_mean, float* S_out, float div, int32_t d, void* workspace,
+                   lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(g && X && peers_host, "NULL argument");
+  LGX_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "n_peers must be in [1, 16]");
+  LGX_REQUIRE(d > 0 && d <= 512, "d must be in [1, 512]");
+  LGX_REQUIRE(!S_out || S_in, "S_out needs S_in");
+  LGX_REQUIRE(!store_mean || S_out, "store_mean needs S_out");
+  LGX_REQUIRE(g->n_partials == 0 || workspace, "graph has split rows: workspace required");
+  LGX_REQUIRE(div != 0.0f && row_offset >= 0, "bad div / row_offset");
+  PeerOut po{};
+  for (int p = 0; p < n_peers; ++p) {
+    LGX_REQUIRE(peers_host[p] != nullptr, "NULL peer pointer");
+    po.ptr[p] = peers_host[p];
+  }
+  po.n = n_peers; po.store_mean = store_mean; po.row_offset = row_offset;
+  return spmm_impl(g, X, S_in, nullptr, S_out, div, d, workspace, (cudaStream_t)stream, po);
+}
+
+int lgx_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(ptr && handle64 && bytes > 0, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  LGX_CHECK_CUDA(cudaMalloc(ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    set_error(std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(e));
+    return LGX_ERR_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  return LGX_OK;
+}
+
+int lgx_peer_open(const unsigned char* handle64, void** ptr) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(ptr && handle64, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  LGX_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return LGX_OK;
+}
+
+int lgx_peer_close(void* ptr) {
+  if (ptr) LGX_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return LGX_OK;
+}
+
+int lgx_peer_free(void* ptr) {
+  if (ptr) LGX_CHECK_CUDA(cudaFree(ptr));
+  return LGX_OK;
 }
 
 size_t lgx_propagate_workspace_bytes(const lgx_graph* g, int32_t d, int32_t n_layers) {

@@ -95,6 +95,23 @@ size_t lgx_spmm_workspace_bytes(const lgx_graph* g, int32_t d);
 int lgx_spmm(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out,
              float div, int32_t d, void* workspace, lgx_stream stream);
 
+/* Fused SpMM + all-gather for row-sharded propagation (the reference's fold loop + torch.cat,
+ * PT/model.py:164-169, across GPUs): the epilogue stores this rank's output rows straight into EVERY
+ * rank's copy of the gathered layer over NVLink peer memory, at rows [row_offset, row_offset + n_rows).
+ *   peers_host : HOST array of n_peers device pointers (own buffer included), each [n_total_rows, d] fp32,
+ *                obtained with lgx_peer_alloc / lgx_peer_open (CUDA IPC, one process per GPU, one node);
+ *   store_mean : 0 -> peers receive acc (next layer's input); 1 -> peers receive (S_in + acc) / div.
+ * The caller separates layers with a cross-rank barrier (all writers done before anyone reads). */
+int lgx_spmm_peers(const lgx_graph* g, const float* X, const float* S_in, float* const* peers_host,
+                   int32_t n_peers, int64_t row_offset, int32_t store_mean, float* S_out, float div,
+                   int32_t d, void* workspace, lgx_stream stream);
+/* Peer-visible device allocations: alloc returns the pointer and a 64-byte IPC handle to send to the
+ * other ranks, which map it with lgx_peer_open (and unmap with lgx_peer_close). */
+int lgx_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int lgx_peer_open(const unsigned char* handle64, void** ptr);
+int lgx_peer_close(void* ptr);
+int lgx_peer_free(void* ptr);
+
 /* LightGCN.computer() (PT/model.py:145-177): out = mean(E0, A E0, ..., A^L E0), E0 = cat(users, items).
  * workspace: lgx_propagate_workspace_bytes(g, d, L) (two [n,d] ping-pong layers + spmm workspace).
  * layers_out (optional): [L, n, d] receives every layer's embeddings. Square graphs only. */

@@ -28,14 +28,19 @@ def _worker(rank, world, port, out_dir):
     ds = dataloader.InteractionDataset(nu, mi, u, i, device=dev)
     m = model.LightGCN(cfg, ds).to(dev).eval()
     g = ds.getGraphHandle()
-    eng = parallel.ShardedEngine(g, nu, mi, d, L, rank, world, dev)
     E0 = m._flat_if_fused()
     users = torch.arange(nu, device=dev)
     with torch.no_grad():
         lu, li = m.computer()
-        light = eng.propagate(E0)
         ref = torch.cat([lu, li])
-        assert (light - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+        for mode in ("fused", "replicated", "allgather"):          # every exchange variant gives the 1-GPU result
+            eng = parallel.ShardedEngine(g, nu, mi, d, L, rank, world, dev, propagate=mode)
+            assert eng.mode == mode
+            for rep in range(2):                                    # twice: buffers are reused across calls
+                light = eng.propagate(E0)
+                assert (light - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (mode, rep)
+            if mode != "allgather":
+                eng.close()
         for mode in ("fp32", "bf16x3"):
             idx1, val1 = m.topk(users, k, mode=mode)
             for shard in ("items", "users"):
@@ -45,6 +50,7 @@ def _worker(rank, world, port, out_dir):
         same = (idx == m.topk(users, k, mode="bf16x3")[0]).float().mean().item()
         assert same > 0.999                                               # propagate differs in the last ulp only
     torch.cuda.synchronize()
+    eng.close()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
