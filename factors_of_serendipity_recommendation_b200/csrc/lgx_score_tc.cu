@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "lgx_common.cuh"
 #include "lgx_score_plan.cuh"

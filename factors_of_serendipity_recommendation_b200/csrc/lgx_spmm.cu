@@ -379,12 +379,14 @@ static int blocks_for(K kernel, int threads) {
 
 struct SpmmTuning {
   int variant;      // kernel variant for d = 64 (see spmm_impl)
+  int variant128;   // kernel variant for d = 128
   int hot_degree;   // columns with at least this degree are kept in L1 (HOT variants)
 };
 static SpmmTuning tuning() {
   static SpmmTuning t = [] {
-    SpmmTuning x{0, 256};
+    SpmmTuning x{0, 0, 256};
     if (const char* e = getenv("LGX_SPMM_VARIANT")) x.variant = atoi(e);
+    if (const char* e = getenv("LGX_SPMM_VARIANT128")) x.variant128 = atoi(e);
     if (const char* e = getenv("LGX_SPMM_HOT_DEGREE")) x.hot_degree = std::max(1, atoi(e));
     return x;
   }();
@@ -435,7 +437,17 @@ static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, floa
       // default: compile-time row stride, 4 gathers in flight per lane, >= 4 CTAs per SM
       // (B200 sweep over U x occupancy at Amazon-Book shape: profiles/r1_spmm_sweep.txt)
       if (d == 64) launch_fixed<16, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
-      else if (d == 128) launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
+      else if (d == 128) {
+        switch (tuning().variant128) {   // LGX_SPMM_VARIANT128: experiment knob for d = 128
+          case 1: launch_fixed<32, 1, 8, 3>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          case 2: launch_fixed<32, 1, 8, 2>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          case 3: launch_fixed<32, 1, 4, 5>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          case 4: launch_fixed<32, 1, 2, 6>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          case 5: launch_fixed<32, 1, 16, 2>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          case 6: launch_fixed<32, 1, 8, 4>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          default: launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+        }
+      }
       else if (d == 256) launch_fixed<32, 2, 4, 3>(g, X, S_in, Y, S_out, partial, div, st, po);
       else if (d == 32) launch_fixed<8, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
       else launch_fixed<4, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);

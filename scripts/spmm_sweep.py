@@ -30,7 +30,7 @@ cold = run(True)
 warm = run(False)
 layer_bytes = g.nnz * 8 + (g.n_rows + 1) * 4 + 2 * g.n_rows * d * 4
 fwd_bytes = 3 * layer_bytes + g.n_rows * d * 4
-print(json.dumps({"variant": os.environ.get("LGX_SPMM_VARIANT", "0"), "hot": os.environ.get("LGX_SPMM_HOT_DEGREE", "-"),
+print(json.dumps({"variant": os.environ.get("LGX_SPMM_VARIANT", "0") + "/" + os.environ.get("LGX_SPMM_VARIANT128", "0"), "hot": os.environ.get("LGX_SPMM_HOT_DEGREE", "-"),
                   "chunk": g.chunk_nnz, "n_long": g.n_long, "shape": name,
                   "cold_ms_med": round(cold[0], 4), "cold_ms_min": round(cold[1], 4), "warm_ms_med": round(warm[0], 4),
                   "cold_gbs": round(fwd_bytes / cold[0] / 1e6, 1), "warm_gbs": round(fwd_bytes / warm[0] / 1e6, 1),
