@@ -74,6 +74,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def measured_traffic(workload, mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/traffic.json, written by scripts/summarize_profile.py); None when no capture exists."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p)).get(f"{workload}:{mode}", {})
+    return t.get("spmm_layer_bytes"), t.get("score_bytes")
+
+
 def spmm_algorithmic_bytes(n_nodes, nnz, d, n_layers):
     """per layer nnz*(4+4) + (N+1)*4 + 2*N*d*4; forward adds one write of the mean."""
     layer = nnz * 8 + (n_nodes + 1) * 4 + 2 * n_nodes * d * 4
@@ -316,19 +326,24 @@ def run_ours(args, shape):
 
     if rank == 0:
         layer_bytes, fwd_bytes = spmm_algorithmic_bytes(N, nnz, d, N_LAYERS)
-        spmm_gbs = fwd_bytes / (t_prop_mean * 1e-3) / 1e9
+        spmm_gbs = layer_bytes / (t_prop_mean / N_LAYERS * 1e-3) / 1e9       # per layer launch (dominant SpMM kernel)
         flops = 2.0 * n_score * mi * d
         score_tf = flops / (t_score_mean * 1e-3) / 1e12
+        tr_spmm, tr_score = measured_traffic(args.workload, mode) if world_size == 1 else (None, None)
         roof_spmm = {"bound": "hbm", "achieved": spmm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": spmm_gbs / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                     "kernel": "k_spmm<16,1> x3 (+ long-row reduce)", "launch_ms": t_prop_mean,
-                     "algorithmic_bytes": fwd_bytes,
+                     "frac": spmm_gbs / peaks["hbm"], "traffic": tr_spmm, "peak_source": peaks["src"],
+                     "kernel": "k_spmm_fixed x3 (+ k_spmm_long); achieved/traffic are per layer launch: "
+                               "algorithmic bytes of one layer / (propagation time / layers)",
+                     "launch_ms": t_prop_mean / N_LAYERS, "algorithmic_bytes": layer_bytes,
+                     "gather_ceiling_note": "random row gathers top out at 17-18.5 TB/s from L2 / 7.1 TB/s from HBM "
+                                            "(profiles/r1_l2_gather_probe.txt)",
                      "no_reuse_gather_bytes": N_LAYERS * (nnz * (8 + 4 * d) + N * d * 4)}
         roof_score = {"bound": "tensor", "achieved": score_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                      "frac": score_tf / peaks["tf_burst"], "traffic": None, "peak_source": peaks["src"] + " (burst)",
+                      "frac": score_tf / peaks["tf_burst"], "traffic": tr_score, "peak_source": peaks["src"] + " (burst)",
                       "kernel": "k_score_topk_tc + merge" if mode_id else "k_score_topk_fp32 + merge",
                       "launch_ms": t_score_mean, "algorithmic_flops": flops}
         dominant = roof_score if t_score_mean >= t_prop_mean else roof_spmm
+        # our kernels per step: L x (k_spmm_fixed [+ k_spmm_long]) + 2 x k_pack (bf16 modes) + score + merge
         launches_per_step = N_LAYERS * (1 + (1 if g.n_long > 0 else 0)) + (2 if mode_id else 0) + 2
         line = {
             "metric": "users scored top-20/sec (3-layer propagation + full-catalogue scoring)",

@@ -8,6 +8,6 @@ python bench.py --mode bf16x3 --no-cpu > gpurun_out/BENCH_${R}_ours_bf16x3.json 
 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain_${R}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launch_${R}.log 2>&1
 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain_${R}b.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'^k_spmm$|k_score_topk_tc' -s 12 -c 4 -o gpurun_out/${R}_prof python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_full_${R}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_spmm_fixed|k_score_topk_tc' -s 8 -c 8 -o gpurun_out/${R}_prof python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_full_${R}.log 2>&1
 tail -2 gpurun_out/ncu_full_${R}.log | cut -c1-200
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${R}_nvsmi.csv

@@ -38,5 +38,19 @@ with open(f"profiles/{R}_ncu_full_summary.txt", "w") as f:
             if k in H:
                 i = H.index(k)
                 f.write(f"{k:75s} {r[i][:110]:>20s} {units[i]}\n")
+# measured DRAM traffic per launch for bench.py's roofline.traffic
+import json, os
+tr = {}
+ir, iw, ik = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("Kernel Name")
+def to_bytes(v, unit):
+    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+sp = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:] if r[ik].startswith("void k_spmm") or r[ik].startswith("k_spmm_fixed")]
+sc = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:] if "k_score_topk_tc" in r[ik]]
+key = os.environ.get("LGX_TRAFFIC_KEY", "amazon-book:bf16")
+path = "profiles/traffic.json"
+alltr = json.load(open(path)) if os.path.exists(path) else {}
+alltr[key] = {"spmm_layer_bytes": sum(sp) / len(sp) if sp else None, "score_bytes": sum(sc) / len(sc) if sc else None,
+              "source": f"profiles/{R}_ncu_full_summary.txt"}
+json.dump(alltr, open(path, "w"), indent=1)
 print(open(f"profiles/{R}_launch_list_summary.txt").read())
 print(open(f"profiles/{R}_ncu_full_summary.txt").read())
