@@ -40,6 +40,10 @@ _SIGS = {
     "lgx_propagate_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "lgx_propagate_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "lgx_propagate_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "lgx_graph_enable_dropout": (C.c_int, [_P, _P]),
+    "lgx_dropout_mask": (C.c_int, [_P, C.c_float, C.c_uint64, C.c_int32, _P, _P]),
+    "lgx_propagate_fwd_dropout": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, _P]),
+    "lgx_propagate_bwd_dropout": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, _P]),
     "lgx_score_dense": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "lgx_pack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "lgx_pack_operand": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
@@ -203,7 +207,18 @@ class Graph:
             check(lib().lgx_spmm_peers(self.handle, ptr(X), ptr(S_in), arr, len(peer_ptrs), row_offset, int(store_mean),
                                        ptr(S_out), div, d, ptr(ws), stream()))
 
-    def propagate_fwd(self, E0: torch.Tensor, n_layers: int, out=None, layers_out=None) -> torch.Tensor:
+    def enable_dropout(self):
+        with torch.cuda.device(self.device):
+            check(lib().lgx_graph_enable_dropout(self.handle, stream()))
+
+    def dropout_mask(self, keep_prob: float, seed: int, transpose: bool = False) -> torch.Tensor:
+        out = torch.empty(self.nnz, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().lgx_dropout_mask(self.handle, keep_prob, seed, int(transpose), ptr(out), stream()))
+        return out
+
+    def propagate_fwd(self, E0: torch.Tensor, n_layers: int, out=None, layers_out=None, dropout=None) -> torch.Tensor:
+        """dropout = (keep_prob, seed): propagate through the edge-dropped graph of that seed."""
         require_cuda(E0, out, layers_out)
         if E0.dtype != torch.float32 or E0.shape[0] != self.n_rows:
             raise ValueError("E0 must be fp32 [n_rows, d]")
@@ -212,17 +227,25 @@ class Graph:
             out = torch.empty_like(E0)
         ws = self.workspace(lib().lgx_propagate_workspace_bytes(self.handle, d, n_layers), ("prop", d))
         with torch.cuda.device(self.device):
-            check(lib().lgx_propagate_fwd(self.handle, ptr(E0), ptr(out), ptr(layers_out), n_layers, d, ptr(ws), stream()))
+            if dropout is not None:
+                check(lib().lgx_propagate_fwd_dropout(self.handle, ptr(E0), ptr(out), n_layers, d, float(dropout[0]),
+                                                      int(dropout[1]), ptr(ws), stream()))
+            else:
+                check(lib().lgx_propagate_fwd(self.handle, ptr(E0), ptr(out), ptr(layers_out), n_layers, d, ptr(ws), stream()))
         return out
 
-    def propagate_bwd(self, g_scaled: torch.Tensor, n_layers: int, out=None) -> torch.Tensor:
+    def propagate_bwd(self, g_scaled: torch.Tensor, n_layers: int, out=None, dropout=None) -> torch.Tensor:
         require_cuda(g_scaled, out)
         d = g_scaled.shape[1]
         if out is None:
             out = torch.empty_like(g_scaled)
         ws = self.workspace(lib().lgx_propagate_workspace_bytes(self.handle, d, n_layers), ("prop", d))
         with torch.cuda.device(self.device):
-            check(lib().lgx_propagate_bwd(self.handle, ptr(g_scaled), ptr(out), n_layers, d, ptr(ws), stream()))
+            if dropout is not None:
+                check(lib().lgx_propagate_bwd_dropout(self.handle, ptr(g_scaled), ptr(out), n_layers, d, float(dropout[0]),
+                                                      int(dropout[1]), ptr(ws), stream()))
+            else:
+                check(lib().lgx_propagate_bwd(self.handle, ptr(g_scaled), ptr(out), n_layers, d, ptr(ws), stream()))
         return out
 
     # ---- sampler

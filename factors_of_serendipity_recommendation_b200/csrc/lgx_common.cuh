@@ -49,6 +49,27 @@ struct WorkItem {
 };
 static_assert(sizeof(WorkItem) == 16, "WorkItem is read as one int4");
 
+// Edge dropout (LightGCN.__dropout_x, PT/model.py:125-143): entry k of A_hat is kept iff
+// hash(seed, pos(k)) < keep_prob and then scaled by 1/keep_prob.  pos(k) = k for the forward pass and
+// the mirrored entry's position for the backward pass (the dropped graph is not symmetric any more).
+struct DropSpec {
+  const int32_t* tpos;   // NULL: pos(k) = k
+  uint64_t seed;
+  float keep_prob;
+  float inv_keep;
+  int enabled;
+};
+__host__ __device__ __forceinline__ uint64_t lgx_mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ bool lgx_keep(uint64_t seed, int64_t pos, float keep_prob) {
+  const uint32_t r = (uint32_t)(lgx_mix64(seed ^ lgx_mix64((uint64_t)pos)) >> 40);   // 24 random bits
+  return (float)r * (1.0f / 16777216.0f) < keep_prob;
+}
+
 // A row that was split into several units; reduced in fixed order by the long-row kernel.
 struct LongRow {
   int32_t row;
@@ -73,4 +94,5 @@ struct lgx_graph {
   int32_t* row_order = nullptr;  // [n_rows] stable degree-descending
   lgx::WorkItem* work = nullptr; // [n_work]
   lgx::LongRow* long_rows = nullptr;  // [n_long]
+  int32_t* tpos = nullptr;            // [nnz] position of the mirrored entry (built on demand for dropout)
 };

@@ -161,6 +161,26 @@ __global__ void k_fill_work(const int32_t* __restrict__ order, const int64_t* __
   if (lane == 0) long_rows[long_off[s]] = LongRow{row, (int32_t)p0, (int32_t)nu, 0};
 }
 
+// tpos[k] = position of entry (col, row) for entry k = (row, col); one warp per row
+__global__ void k_transpose_pos(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n_rows,
+                                int32_t* __restrict__ tpos, int* __restrict__ bad) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  for (int64_t k = indptr[r] + lane; k < indptr[r + 1]; k += 32) {
+    const int32_t c = indices[k];
+    int64_t lo = indptr[c], hi = indptr[c + 1];
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (indices[mid] < (int32_t)r) lo = mid + 1; else hi = mid; }
+    if (lo < indptr[c + 1] && indices[lo] == (int32_t)r) tpos[k] = (int32_t)lo; else { tpos[k] = (int32_t)k; *bad = 1; }
+  }
+}
+
+__global__ void k_dropout_mask(int64_t nnz, const int32_t* __restrict__ tpos, uint64_t seed, float keep_prob,
+                               uint8_t* __restrict__ out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+    out[k] = lgx_keep(seed, tpos ? (int64_t)tpos[k] : k, keep_prob) ? 1 : 0;
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)sm_count() * 32;
@@ -171,7 +191,7 @@ static inline int grid_exact(int64_t n, int block) { return (int)std::max<int64_
 static void free_graph(lgx_graph* g) {
   if (!g) return;
   cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->values); cudaFree(g->degree);
-  cudaFree(g->dinv); cudaFree(g->row_order); cudaFree(g->work); cudaFree(g->long_rows);
+  cudaFree(g->dinv); cudaFree(g->row_order); cudaFree(g->work); cudaFree(g->long_rows); cudaFree(g->tpos);
   delete g;
 }
 
@@ -422,6 +442,43 @@ int lgx_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_
     return rc;
   }
   *out = g;
+  return LGX_OK;
+}
+
+int lgx_graph_enable_dropout(lgx_graph* g, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(g, "graph is NULL");
+  if (g->tpos) return LGX_OK;
+  LGX_REQUIRE(g->n_rows == g->n_cols, "dropout needs the square (symmetric-structure) graph");
+  LGX_REQUIRE(g->nnz < ((int64_t)1 << 31), "dropout positions are int32: nnz must be < 2^31");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* d_bad = nullptr;
+  LGX_CHECK_CUDA(cudaMalloc(&g->tpos, sizeof(int32_t) * std::max<int64_t>(1, g->nnz)));
+  LGX_CHECK_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+  LGX_CHECK_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  k_transpose_pos<<<grid_exact(g->n_rows * 32, 256), 256, 0, st>>>(g->indptr, g->indices, g->n_rows, g->tpos, d_bad);
+  int bad = 0;
+  LGX_CHECK_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LGX_CHECK_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_bad);
+  if (bad) {
+    cudaFree(g->tpos);
+    g->tpos = nullptr;
+    set_error("invalid argument: the graph's sparsity pattern is not symmetric (dropout backward needs mirrored entries)");
+    return LGX_ERR_INVALID;
+  }
+  return LGX_OK;
+}
+
+int lgx_dropout_mask(const lgx_graph* g, float keep_prob, uint64_t seed, int32_t transpose, uint8_t* mask,
+                     lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(g && mask, "NULL argument");
+  LGX_REQUIRE(!transpose || g->tpos, "call lgx_graph_enable_dropout first");
+  if (g->nnz > 0)
+    k_dropout_mask<<<grid_for(g->nnz, 256), 256, 0, (cudaStream_t)stream>>>(g->nnz, transpose ? g->tpos : nullptr, seed,
+                                                                           keep_prob, mask);
+  LGX_CHECK_LAUNCH();
   return LGX_OK;
 }
 

@@ -31,6 +31,12 @@ __device__ __forceinline__ float ld_stream_f32(const float* p) {
 }
 __device__ __forceinline__ float4 ld_gather_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+__device__ __forceinline__ float drop_value(const DropSpec& drop, int64_t k, float a) {
+  if (!drop.enabled) return a;
+  const int64_t pos = drop.tpos ? (int64_t)__ldg(drop.tpos + k) : k;
+  return lgx_keep(drop.seed, pos, drop.keep_prob) ? a * drop.inv_keep : 0.f;
+}
+
 __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
   a.x = fmaf(v, x.x, a.x);
   a.y = fmaf(v, x.y, a.y);
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(256, MINB)
 k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
        const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
        float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d,
-       const float* __restrict__ dinv, float hot_rsqrt) {
+       const float* __restrict__ dinv, float hot_rsqrt, const DropSpec drop) {
   static_assert(G % U == 0 || U > G, "U must divide G");
   constexpr int UU = U > G ? G : U;
   const int lig = threadIdx.x & (G - 1);
@@ -128,7 +134,7 @@ k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, co
     float a_nxt = 0.f;
     if (lig < len) {
       c_nxt = ld_stream_i32(indices + start + lig);
-      a_nxt = ld_stream_f32(values + start + lig);
+      a_nxt = drop_value(drop, start + lig, ld_stream_f32(values + start + lig));
     }
     for (int base = 0; base < maxlen; base += G) {
       const int32_t c = c_nxt;
@@ -137,7 +143,7 @@ k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, co
       c_nxt = 0; a_nxt = 0.f;
       if (kn < len) {
         c_nxt = ld_stream_i32(indices + start + kn);
-        a_nxt = ld_stream_f32(values + start + kn);
+        a_nxt = drop_value(drop, start + kn, ld_stream_f32(values + start + kn));
       }
       const int cnt = len - base;  // may be <= 0 for the shorter group of the warp
 #pragma unroll
@@ -190,11 +196,14 @@ k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, co
 // and steps in which every group of the warp has a full batch of G non-zeros run without any
 // predication.  (ncu on the generic kernel: 38 warp instructions per non-zero step, 64% issue-active
 // -- the gather loop was instruction-bound, not memory-bound.)
-template <int G, int V, int U, int MINB>
+// MODE bit 0: peer output (fused all-gather), bit 1: edge dropout.  Separate instantiations: with runtime
+// flags the plain path lost 4% (peer check per row) + 5% (dropout check per index batch).
+template <int G, int V, int U, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB)
 k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
              const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
-             float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, const PeerOut po) {
+             float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, const PeerOut po,
+             const DropSpec drop) {
   constexpr int D4 = G * V;            // float4 per embedding row
   constexpr int D = 4 * D4;
   constexpr int UU = U > G ? G : U;
@@ -208,11 +217,12 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
     const int64_t item = round * n_groups + group;
     const int32_t* ci = indices;
     const float* cv = values;
+    int64_t start = 0;
     int32_t row = 0, len = 0, part = -1;
     const bool have = item < n_work;
     if (have) {
       const int4 w0 = __ldg(reinterpret_cast<const int4*>(work + item));        // start (lo, hi), row, len
-      const int64_t start = ((int64_t)(uint32_t)w0.x) | ((int64_t)w0.y << 32);
+      start = ((int64_t)(uint32_t)w0.x) | ((int64_t)w0.y << 32);
       ci += start; cv += start;
       row = w0.z; len = w0.w;
       part = item < n_partials ? (int32_t)item : -1;
@@ -227,13 +237,21 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
 
     int32_t c_nxt = 0;
     float a_nxt = 0.f;
-    if (lig < len) { c_nxt = ld_stream_i32(ci + lig); a_nxt = ld_stream_f32(cv + lig); }
+    if (lig < len) {
+      c_nxt = ld_stream_i32(ci + lig);
+      a_nxt = ld_stream_f32(cv + lig);
+      if (MODE & 2) a_nxt = drop_value(drop, start + lig, a_nxt);
+    }
     for (int base = 0; base < maxlen; base += G) {
       const int32_t c = c_nxt;
       const float a = a_nxt;
       const int kn = base + G + lig;
       c_nxt = 0; a_nxt = 0.f;
-      if (kn < len) { c_nxt = ld_stream_i32(ci + kn); a_nxt = ld_stream_f32(cv + kn); }
+      if (kn < len) {
+        c_nxt = ld_stream_i32(ci + kn);
+        a_nxt = ld_stream_f32(cv + kn);
+        if (MODE & 2) a_nxt = drop_value(drop, start + kn, a_nxt);
+      }
       const int cnt = len - base;
       if (__all_sync(0xffffffffu, cnt >= G)) {
         // ---- full batch in every group of the warp: no predicates
@@ -285,7 +303,7 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
           *reinterpret_cast<float4*>(partial + (int64_t)part * D + col) = acc[v];
         } else {
           const float4 mean = epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
-          if (po.n > 0) peer_store4(po, row, D, col, acc[v], mean);
+          if (MODE & 1) peer_store4(po, row, D, col, acc[v], mean);
         }
       }
     }
@@ -296,7 +314,7 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
 __global__ void __launch_bounds__(256)
 k_spmm_scalar(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
               const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
-              float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d) {
+              float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, int d, const DropSpec drop) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -307,7 +325,7 @@ k_spmm_scalar(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_parti
       float acc = 0.f;
       for (int k = 0; k < w.len; ++k) {
         const int32_t c = indices[w.start + k];
-        acc = fmaf(values[w.start + k], __ldg(X + (int64_t)c * d + c0), acc);
+        acc = fmaf(drop_value(drop, w.start + k, values[w.start + k]), __ldg(X + (int64_t)c * d + c0), acc);
       }
       if (part >= 0) {
         partial[part * d + c0] = acc;
@@ -395,7 +413,7 @@ static SpmmTuning tuning() {
 
 template <int G, int V, bool EXACT, int U, int MINB, bool HOT>
 static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
-                        float div, int d, cudaStream_t st) {
+                        float div, int d, cudaStream_t st, const DropSpec& drop) {
   static int max_blocks = 0;
   if (max_blocks == 0) max_blocks = blocks_for(k_spmm<G, V, EXACT, U, MINB, HOT>, 256);
   const int64_t groups_per_block = 256 / G;
@@ -403,23 +421,33 @@ static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, f
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
   const float hot_rsqrt = 1.0f / sqrtf((float)tuning().hot_degree);
   k_spmm<G, V, EXACT, U, MINB, HOT><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values,
-                                                           X, S_in, Y, S_out, partial, div, d, g->dinv, hot_rsqrt);
+                                                           X, S_in, Y, S_out, partial, div, d, g->dinv, hot_rsqrt, drop);
 }
 
-template <int G, int V, int U, int MINB>
-static void launch_fixed(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
-                         float div, cudaStream_t st, const PeerOut& po = PeerOut{}) {
+template <int G, int V, int U, int MINB, int MODE>
+static void launch_fixed_t(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
+                           float div, cudaStream_t st, const PeerOut& po, const DropSpec& drop) {
   static int max_blocks = 0;
-  if (max_blocks == 0) max_blocks = blocks_for(k_spmm_fixed<G, V, U, MINB>, 256);
+  if (max_blocks == 0) max_blocks = blocks_for(k_spmm_fixed<G, V, U, MINB, MODE>, 256);
   const int64_t groups_per_block = 256 / G;
   const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
-  k_spmm_fixed<G, V, U, MINB><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in,
-                                                     Y, S_out, partial, div, po);
+  k_spmm_fixed<G, V, U, MINB, MODE><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X,
+                                                           S_in, Y, S_out, partial, div, po, drop);
+}
+template <int G, int V, int U, int MINB>
+static void launch_fixed(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
+                         float div, cudaStream_t st, const PeerOut& po, const DropSpec& drop) {
+  const int mode = (po.n > 0 ? 1 : 0) | (drop.enabled ? 2 : 0);
+  if (mode == 0) launch_fixed_t<G, V, U, MINB, 0>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+  else if (mode == 1) launch_fixed_t<G, V, U, MINB, 1>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+  else if (mode == 2) launch_fixed_t<G, V, U, MINB, 2>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+  else launch_fixed_t<G, V, U, MINB, 3>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
 }
 
 static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div,
-                     int32_t d, void* workspace, cudaStream_t st, const PeerOut& po = PeerOut{}) {
+                     int32_t d, void* workspace, cudaStream_t st, const PeerOut& po = PeerOut{},
+                     const DropSpec& drop = DropSpec{}) {
   float* partial = reinterpret_cast<float*>(workspace);
   const bool fixed_ok = (d == 16 || d == 32 || d == 64 || d == 128 || d == 256) &&
                         g->n_cols * (int64_t)(d / 4) < ((int64_t)1 << 32);
@@ -432,53 +460,53 @@ static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, floa
     if (d % 4 != 0) {
       const int64_t need = (g->n_work + 7) / 8;
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
-      k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d);
+      k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d, drop);
     } else if ((tuning().variant == 0 || po.n > 0) && fixed_ok) {
       // default: compile-time row stride, 4 gathers in flight per lane, >= 4 CTAs per SM
       // (B200 sweep over U x occupancy at Amazon-Book shape: profiles/r1_spmm_sweep.txt)
-      if (d == 64) launch_fixed<16, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
+      if (d == 64) launch_fixed<16, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
       else if (d == 128) {
         switch (tuning().variant128) {   // LGX_SPMM_VARIANT128: experiment knob for d = 128
-          case 1: launch_fixed<32, 1, 8, 3>(g, X, S_in, Y, S_out, partial, div, st, po); break;
-          case 2: launch_fixed<32, 1, 8, 2>(g, X, S_in, Y, S_out, partial, div, st, po); break;
-          case 3: launch_fixed<32, 1, 4, 5>(g, X, S_in, Y, S_out, partial, div, st, po); break;
-          case 4: launch_fixed<32, 1, 2, 6>(g, X, S_in, Y, S_out, partial, div, st, po); break;
-          case 5: launch_fixed<32, 1, 16, 2>(g, X, S_in, Y, S_out, partial, div, st, po); break;
-          case 6: launch_fixed<32, 1, 8, 4>(g, X, S_in, Y, S_out, partial, div, st, po); break;
-          default: launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po); break;
+          case 1: launch_fixed<32, 1, 8, 3>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
+          case 2: launch_fixed<32, 1, 8, 2>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
+          case 3: launch_fixed<32, 1, 4, 5>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
+          case 4: launch_fixed<32, 1, 2, 6>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
+          case 5: launch_fixed<32, 1, 16, 2>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
+          case 6: launch_fixed<32, 1, 8, 4>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
+          default: launch_fixed<32, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po, drop); break;
         }
       }
-      else if (d == 256) launch_fixed<32, 2, 4, 3>(g, X, S_in, Y, S_out, partial, div, st, po);
-      else if (d == 32) launch_fixed<8, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
-      else launch_fixed<4, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po);
+      else if (d == 256) launch_fixed<32, 2, 4, 3>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+      else if (d == 32) launch_fixed<8, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+      else launch_fixed<4, 1, 4, 4>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
     } else if (d == 64) {
       switch (tuning().variant) {   // experiment knob LGX_SPMM_VARIANT (scripts/spmm_sweep.py); 0 = default above
-        case 1: launch_spmm<16, 1, true, 8, 3, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 3: launch_spmm<16, 1, true, 16, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 5: if (hot_ok) { launch_spmm<16, 1, true, 8, 2, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
-        case 6: if (hot_ok) { launch_spmm<16, 1, true, 8, 3, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
-        case 7: if (hot_ok) { launch_spmm<16, 1, true, 4, 4, true>(g, X, S_in, Y, S_out, partial, div, d, st); break; }
-        case 12: launch_spmm<16, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
-        case 20: launch_fixed<16, 1, 8, 2>(g, X, S_in, Y, S_out, partial, div, st); break;
-        case 21: launch_fixed<16, 1, 8, 3>(g, X, S_in, Y, S_out, partial, div, st); break;
-        case 24: launch_fixed<16, 1, 8, 4>(g, X, S_in, Y, S_out, partial, div, st); break;
-        case 26: launch_fixed<16, 1, 4, 5>(g, X, S_in, Y, S_out, partial, div, st); break;
-        default: launch_spmm<16, 1, true, 4, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st); break;
+        case 1: launch_spmm<16, 1, true, 8, 3, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break;
+        case 3: launch_spmm<16, 1, true, 16, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break;
+        case 5: if (hot_ok) { launch_spmm<16, 1, true, 8, 2, true>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break; }
+        case 6: if (hot_ok) { launch_spmm<16, 1, true, 8, 3, true>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break; }
+        case 7: if (hot_ok) { launch_spmm<16, 1, true, 4, 4, true>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break; }
+        case 12: launch_spmm<16, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break;
+        case 20: launch_fixed<16, 1, 8, 2>(g, X, S_in, Y, S_out, partial, div, st, PeerOut{}, drop); break;
+        case 21: launch_fixed<16, 1, 8, 3>(g, X, S_in, Y, S_out, partial, div, st, PeerOut{}, drop); break;
+        case 24: launch_fixed<16, 1, 8, 4>(g, X, S_in, Y, S_out, partial, div, st, PeerOut{}, drop); break;
+        case 26: launch_fixed<16, 1, 4, 5>(g, X, S_in, Y, S_out, partial, div, st, PeerOut{}, drop); break;
+        default: launch_spmm<16, 1, true, 4, 4, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop); break;
       }
     } else if (d == 128) {
-      launch_spmm<32, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     } else if (d == 256) {
-      launch_spmm<32, 2, true, 8, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 2, true, 8, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     } else if (d == 32) {
-      launch_spmm<8, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<8, 1, true, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     } else if (d == 16) {
-      launch_spmm<4, 1, true, 4, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<4, 1, true, 4, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     } else if (d <= 128) {
-      launch_spmm<32, 1, false, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 1, false, 8, 2, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     } else if (d <= 256) {
-      launch_spmm<32, 2, false, 8, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 2, false, 8, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     } else {
-      launch_spmm<32, 4, false, 4, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st);
+      launch_spmm<32, 4, false, 4, 1, false>(g, X, S_in, Y, S_out, partial, div, d, st, drop);
     }
     LGX_CHECK_LAUNCH();
   }
@@ -578,8 +606,10 @@ size_t lgx_propagate_workspace_bytes(const lgx_graph* g, int32_t d, int32_t n_la
   return 2 * layer + lgx_spmm_workspace_bytes(g, d);
 }
 
-int lgx_propagate_fwd(const lgx_graph* g, const float* E0, float* out_mean, float* layers_out, int32_t n_layers,
-                      int32_t d, void* workspace, lgx_stream stream) {
+static int make_drop(const lgx_graph* g, float keep_prob, uint64_t seed, bool transpose, DropSpec* out);
+
+static int propagate_fwd_impl(const lgx_graph* g, const float* E0, float* out_mean, float* layers_out, int32_t n_layers,
+                              int32_t d, void* workspace, lgx_stream stream, const DropSpec& drop) {
   LGX_CHECK_DEVICE();
   LGX_REQUIRE(g && E0 && out_mean, "NULL argument");
   LGX_REQUIRE(g->n_rows == g->n_cols, "propagate needs a square graph (use lgx_spmm for row shards)");
@@ -601,7 +631,7 @@ int lgx_propagate_fwd(const lgx_graph* g, const float* E0, float* out_mean, floa
     const bool last = l == n_layers;
     float* Y = layers_out ? layers_out + (size_t)(l - 1) * n_el : (last ? nullptr : buf[(l - 1) & 1]);
     const float div = last ? (float)(n_layers + 1) : 1.0f;  // torch.mean = sum / (L+1), PT/model.py:175
-    int rc = spmm_impl(g, X, S_in, Y, out_mean, div, d, spmm_ws, st);
+    int rc = spmm_impl(g, X, S_in, Y, out_mean, div, d, spmm_ws, st, PeerOut{}, drop);
     if (rc != LGX_OK) return rc;
     X = Y;
     S_in = out_mean;
@@ -609,8 +639,30 @@ int lgx_propagate_fwd(const lgx_graph* g, const float* E0, float* out_mean, floa
   return LGX_OK;
 }
 
-int lgx_propagate_bwd(const lgx_graph* g, const float* g_scaled, float* dE0, int32_t n_layers, int32_t d,
-                      void* workspace, lgx_stream stream) {
+int lgx_propagate_fwd(const lgx_graph* g, const float* E0, float* out_mean, float* layers_out, int32_t n_layers,
+                      int32_t d, void* workspace, lgx_stream stream) {
+  return propagate_fwd_impl(g, E0, out_mean, layers_out, n_layers, d, workspace, stream, DropSpec{});
+}
+
+int lgx_propagate_fwd_dropout(const lgx_graph* g, const float* E0, float* out_mean, int32_t n_layers, int32_t d,
+                              float keep_prob, uint64_t seed, void* workspace, lgx_stream stream) {
+  LGX_REQUIRE(g, "graph is NULL");
+  DropSpec drop{};
+  int rc = make_drop(g, keep_prob, seed, false, &drop);
+  if (rc != LGX_OK) return rc;
+  return propagate_fwd_impl(g, E0, out_mean, nullptr, n_layers, d, workspace, stream, drop);
+}
+
+static int make_drop(const lgx_graph* g, float keep_prob, uint64_t seed, bool transpose, DropSpec* out) {
+  LGX_REQUIRE(keep_prob > 0.0f && keep_prob <= 1.0f, "keep_prob must be in (0, 1]");
+  LGX_REQUIRE(!transpose || g->tpos, "call lgx_graph_enable_dropout before the dropout backward");
+  out->tpos = transpose ? g->tpos : nullptr;
+  out->seed = seed; out->keep_prob = keep_prob; out->inv_keep = 1.0f / keep_prob; out->enabled = 1;
+  return LGX_OK;
+}
+
+static int propagate_bwd_impl(const lgx_graph* g, const float* g_scaled, float* dE0, int32_t n_layers, int32_t d,
+                              void* workspace, lgx_stream stream, const DropSpec& drop) {
   LGX_CHECK_DEVICE();
   LGX_REQUIRE(g && g_scaled && dE0, "NULL argument");
   LGX_REQUIRE(g->n_rows == g->n_cols, "propagate needs a square graph");
@@ -632,11 +684,27 @@ int lgx_propagate_bwd(const lgx_graph* g, const float* g_scaled, float* dE0, int
   const float* t = g_scaled;
   for (int l = n_layers; l >= 1; --l) {
     float* t_new = (l == 1) ? dE0 : buf[l & 1];
-    int rc = spmm_impl(g, t, g_scaled, nullptr, t_new, 1.0f, d, spmm_ws, st);
+    int rc = spmm_impl(g, t, g_scaled, nullptr, t_new, 1.0f, d, spmm_ws, st, PeerOut{}, drop);
     if (rc != LGX_OK) return rc;
     t = t_new;
   }
   return LGX_OK;
+}
+
+int lgx_propagate_bwd(const lgx_graph* g, const float* g_scaled, float* dE0, int32_t n_layers, int32_t d,
+                      void* workspace, lgx_stream stream) {
+  return propagate_bwd_impl(g, g_scaled, dE0, n_layers, d, workspace, stream, DropSpec{});
+}
+
+// Backward through the DROPPED graph of the same step: dX = (A_drop)^T dY, and entry (i, j) of the
+// transpose carries the keep decision of entry (j, i) -> hash of the mirrored position.
+int lgx_propagate_bwd_dropout(const lgx_graph* g, const float* g_scaled, float* dE0, int32_t n_layers, int32_t d,
+                              float keep_prob, uint64_t seed, void* workspace, lgx_stream stream) {
+  LGX_REQUIRE(g, "graph is NULL");
+  DropSpec drop{};
+  int rc = make_drop(g, keep_prob, seed, true, &drop);
+  if (rc != LGX_OK) return rc;
+  return propagate_bwd_impl(g, g_scaled, dE0, n_layers, d, workspace, stream, drop);
 }
 
 }  // extern "C"

@@ -39,10 +39,10 @@ class _Propagate(torch.autograd.Function):
     (A_hat symmetric, Horner form) -- replaces SparseAddmmBackward0 + the per-call COO re-sort."""
 
     @staticmethod
-    def forward(ctx, flat_w, user_w, item_w, graph, n_layers):
+    def forward(ctx, flat_w, user_w, item_w, graph, n_layers, dropout=None):
         E0 = flat_w if flat_w is not None else torch.cat([user_w, item_w])
-        out = graph.propagate_fwd(E0.detach(), n_layers)
-        ctx.graph, ctx.n_layers, ctx.n_users = graph, n_layers, user_w.shape[0]
+        out = graph.propagate_fwd(E0.detach(), n_layers, dropout=dropout)
+        ctx.graph, ctx.n_layers, ctx.n_users, ctx.dropout = graph, n_layers, user_w.shape[0], dropout
         users, items = out[: ctx.n_users], out[ctx.n_users:]
         return users, items
 
@@ -57,8 +57,8 @@ class _Propagate(torch.autograd.Function):
             torch.mul(g_users, scale, out=g[:n_users])
         if g_items is not None:
             torch.mul(g_items, scale, out=g[n_users:])
-        dE0 = ctx.graph.propagate_bwd(g, ctx.n_layers)
-        return None, dE0[:n_users], dE0[n_users:], None, None
+        dE0 = ctx.graph.propagate_bwd(g, ctx.n_layers, dropout=ctx.dropout)
+        return None, dE0[:n_users], dE0[n_users:], None, None, None
 
 
 class _BprLoss(torch.autograd.Function):
@@ -66,12 +66,12 @@ class _BprLoss(torch.autograd.Function):
     scatter of the row gradients + Horner propagate + reg scatter, no host sync."""
 
     @staticmethod
-    def forward(ctx, flat_w, user_w, item_w, graph, n_layers, users, pos, neg):
+    def forward(ctx, flat_w, user_w, item_w, graph, n_layers, users, pos, neg, dropout=None):
         E0 = (flat_w if flat_w is not None else torch.cat([user_w, item_w])).detach()
         n_users = user_w.shape[0]
-        light = graph.propagate_fwd(E0, n_layers)
+        light = graph.propagate_fwd(E0, n_layers, dropout=dropout)
         out2, coef = _lgx.bpr_forward(light, E0, users, pos, neg, n_users)
-        ctx.graph, ctx.n_layers, ctx.n_users = graph, n_layers, n_users
+        ctx.graph, ctx.n_layers, ctx.n_users, ctx.dropout = graph, n_layers, n_users, dropout
         ctx.save_for_backward(light, E0, users, pos, neg, coef)
         return out2[0], out2[1]
 
@@ -84,10 +84,10 @@ class _BprLoss(torch.autograd.Function):
             G = torch.zeros_like(E0)
             _lgx.bpr_backward_light(light, users, pos, neg, coef, n_users, 1.0 / (L + 1),
                                     g_loss.to(torch.float32).contiguous(), G)
-            ctx.graph.propagate_bwd(G, L, out=dE0)
+            ctx.graph.propagate_bwd(G, L, out=dE0, dropout=ctx.dropout)
         if g_reg is not None:
             _lgx.bpr_backward_reg(E0, users, pos, neg, n_users, 1.0, g_reg.to(torch.float32).contiguous(), dE0)
-        return None, dE0[:n_users], dE0[n_users:], None, None, None, None, None
+        return None, dE0[:n_users], dE0[n_users:], None, None, None, None, None, None
 
 
 def _as_index(t, device):
@@ -158,6 +158,7 @@ class LightGCN(BasicModel):
             self.embedding_user.weight.data.copy_(torch.from_numpy(np.asarray(self.config["user_emb"])))
             self.embedding_item.weight.data.copy_(torch.from_numpy(np.asarray(self.config["item_emb"])))
         self.f = nn.Sigmoid()
+        self._drop_calls = 0       # one fresh edge-dropout seed per computer() call in training mode
         self._flat = None          # one contiguous [N, d] buffer; the two weights are views of it
         self._graph = None
         self._eval_cache = None
@@ -224,23 +225,33 @@ class LightGCN(BasicModel):
         wu, wi = self.embedding_user.weight, self.embedding_item.weight
         return (wu.data_ptr(), wi.data_ptr(), wu._version, wi._version, self.n_layers)
 
+    def _dropout_spec(self):
+        """(keep_prob, seed) for this call when --dropout 1 and training (PT/model.py:154-159), else None.
+        The reference draws torch.rand on the CPU and rebuilds the COO tensor per call; here the keep mask is a
+        counter-based hash evaluated inside the SpMM, one new seed per call (statistical parity)."""
+        if not (self.config["dropout"] and self.training):
+            return None
+        self.graph.enable_dropout()
+        self._drop_calls += 1
+        return (float(self.keep_prob), (int(self.config.get("seed", world.seed)) << 32) + self._drop_calls)
+
     def computer(self):
-        """PT/model.py:145-177.  Edge dropout (config['dropout'], off by default) is not implemented."""
-        if self.config["dropout"] and self.training:
-            raise NotImplementedError("edge dropout (--dropout 1) is a 'next' row (SURVEY.md section 8f-4)")
+        """PT/model.py:145-177."""
         wu, wi = self.embedding_user.weight, self.embedding_item.weight
+        drop = self._dropout_spec()
         need_grad = torch.is_grad_enabled() and (wu.requires_grad or wi.requires_grad)
         if not need_grad:
             key = self._weights_key()
-            if self._eval_cache is not None and self._eval_cache[0] == key:
+            if drop is None and self._eval_cache is not None and self._eval_cache[0] == key:
                 return self._eval_cache[1]
             flat = self._flat_if_fused()
             E0 = flat if flat is not None else torch.cat([wu.detach(), wi.detach()])
-            out = self.graph.propagate_fwd(E0.detach(), self.n_layers)
+            out = self.graph.propagate_fwd(E0.detach(), self.n_layers, dropout=drop)
             res = (out[: self.num_users], out[self.num_users:])
-            self._eval_cache = (key, res)
+            if drop is None:
+                self._eval_cache = (key, res)
             return res
-        return _Propagate.apply(self._flat_if_fused(), wu, wi, self.graph, self.n_layers)
+        return _Propagate.apply(self._flat_if_fused(), wu, wi, self.graph, self.n_layers, drop)
 
     # ---- scoring
     def getUsersRating(self, users):
@@ -288,12 +299,10 @@ class LightGCN(BasicModel):
 
     def bpr_loss(self, users, pos, neg):
         """PT/model.py:196-209 -> (loss, reg_loss), differentiable w.r.t. the two embedding tables."""
-        if self.config["dropout"] and self.training:
-            raise NotImplementedError("edge dropout (--dropout 1) is a 'next' row (SURVEY.md section 8f-4)")
         dev = self.embedding_user.weight.device
         users, pos, neg = _as_index(users, dev), _as_index(pos, dev), _as_index(neg, dev)
         return _BprLoss.apply(self._flat_if_fused(), self.embedding_user.weight, self.embedding_item.weight,
-                              self.graph, self.n_layers, users, pos, neg)
+                              self.graph, self.n_layers, users, pos, neg, self._dropout_spec())
 
     def forward(self, users, items):
         """PT/model.py:211-220."""

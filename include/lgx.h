@@ -123,6 +123,23 @@ int lgx_propagate_fwd(const lgx_graph* g, const float* E0, float* out_mean, floa
 int lgx_propagate_bwd(const lgx_graph* g, const float* g_scaled, float* dE0,
                       int32_t n_layers, int32_t d, void* workspace, lgx_stream stream);
 
+/* Edge dropout (LightGCN.__dropout_x / __dropout, PT/model.py:125-143; --dropout 1, training only).
+ * Every stored entry k of A_hat is kept with probability keep_prob and scaled by 1/keep_prob; the keep
+ * decision is a counter-based hash of (seed, position of the entry), evaluated inside the SpMM -- no
+ * COO rebuild and no CPU torch.rand.  One seed per computer() call: all L layers and the backward of
+ * that call see the same dropped graph.  The dropped graph is not symmetric, so the backward reads the
+ * keep decision of the mirrored entry (positions built once by lgx_graph_enable_dropout).
+ * lgx_dropout_mask exports the mask (uint8[nnz]; transpose = 1: mask of the mirrored entries). */
+int lgx_graph_enable_dropout(lgx_graph* g, lgx_stream stream);
+int lgx_dropout_mask(const lgx_graph* g, float keep_prob, uint64_t seed, int32_t transpose,
+                     uint8_t* mask, lgx_stream stream);
+int lgx_propagate_fwd_dropout(const lgx_graph* g, const float* E0, float* out_mean, int32_t n_layers,
+                              int32_t d, float keep_prob, uint64_t seed, void* workspace,
+                              lgx_stream stream);
+int lgx_propagate_bwd_dropout(const lgx_graph* g, const float* g_scaled, float* dE0, int32_t n_layers,
+                              int32_t d, float keep_prob, uint64_t seed, void* workspace,
+                              lgx_stream stream);
+
 /* --------------------------------------------------------------------------------------- scoring
  * getUsersRating (PT/model.py:179-184): out[b, j] = f(<U[users[b]], I[j]>), f = sigmoid if
  * apply_sigmoid; fp32 CUDA-core arithmetic like the reference's SGEMM.  users may be NULL (rows 0..B-1). */
