@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--workload", default="amazon-book")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--propagate", default="auto", choices=["auto", "fused", "allgather", "replicated"],
+    ap.add_argument("--propagate", default="auto", choices=["auto", "overlap", "fused", "allgather", "replicated"],
                     help="propagation exchange at N > 1 (parallel.ShardedEngine)")
     ap.add_argument("--chunk", type=int, default=0, help="long-row split size for the graph build (0 = default 256)")
     ap.add_argument("--shard", default="auto", choices=["auto", "items", "users"], help="scoring split at N > 1")

@@ -36,6 +36,7 @@ _SIGS = {
     "lgx_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P), C.c_char_p]),
     "lgx_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "lgx_peer_close": (C.c_int, [_P]),
+    "lgx_peer_copy": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_size_t, C.c_size_t, _P]),
     "lgx_peer_free": (C.c_int, [_P]),
     "lgx_propagate_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "lgx_propagate_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
@@ -294,6 +295,13 @@ class PeerBuffer:
             self.tensor = None
             lib().lgx_peer_free(C.c_void_p(self.ptr))
             self.ptr = 0
+
+
+def peer_copy(peer_ptrs, self_rank: int, offset_bytes: int, nbytes: int, cuda_stream, device):
+    """P2P DMA of one byte range of my buffer into every other rank's buffer (one async copy per peer)."""
+    arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+    with torch.cuda.device(device):
+        check(lib().lgx_peer_copy(arr, len(peer_ptrs), self_rank, offset_bytes, nbytes, C.c_void_p(cuda_stream.cuda_stream)))
 
 
 # ------------------------------------------------------------------------------------- free functions

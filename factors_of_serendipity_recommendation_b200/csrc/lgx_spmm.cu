@@ -589,6 +589,20 @@ int lgx_peer_open(const unsigned char* handle64, void** ptr) {
   return LGX_OK;
 }
 
+int lgx_peer_copy(void* const* peers_host, int32_t n_peers, int32_t self, size_t offset_bytes, size_t bytes,
+                  lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(peers_host && n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers, "bad peer list");
+  if (bytes == 0) return LGX_OK;
+  const char* src = reinterpret_cast<const char*>(peers_host[self]) + offset_bytes;
+  for (int k = 1; k < n_peers; ++k) {             // staggered order: rank r starts with r+1 (no hot receiver)
+    const int p = (self + k) % n_peers;
+    char* dst = reinterpret_cast<char*>(peers_host[p]) + offset_bytes;
+    LGX_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));   // one plain async copy per peer
+  }
+  return LGX_OK;
+}
+
 int lgx_peer_close(void* ptr) {
   if (ptr) LGX_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
   return LGX_OK;

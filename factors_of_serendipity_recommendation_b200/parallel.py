@@ -76,13 +76,16 @@ class ShardedEngine:
     """Forward propagation + full-catalogue top-K over ``world`` GPUs (one instance per rank)."""
 
     def __init__(self, graph, n_users: int, m_items: int, d: int, n_layers: int, rank: int, world: int, device,
-                 propagate: str = "auto"):
+                 propagate: str = "auto", chunks: int = 8):
         """propagate = "fused"     : SpMM epilogue stores rows into every rank's gathered buffer over NVLink peer
                                      memory (lgx_spmm_peers) + one barrier per layer;
                        "allgather" : SpMM into a local block + NCCL all_gather_into_tensor per layer;
                        "replicated": every rank propagates the whole graph (no exchange) -- wins when a layer is
                                      cheaper than one collective (Amazon-Book shape: 0.13 ms/layer);
-                       "auto"      : replicated below 64 MB per layer, else fused when d allows, else allgather."""
+                       "overlap"   : every layer in `chunks` row chunks; each finished chunk is written locally and
+                                     pushed to the peers by the copy engines (P2P DMA on a side stream) while the
+                                     next chunk computes;
+                       "auto"      : replicated below 64 MB per layer, else overlap when d allows, else allgather."""
         from . import _lgx
 
         self._lgx = _lgx
@@ -92,7 +95,7 @@ class ShardedEngine:
         self.lo, self.hi = item_shard_bounds(m_items, rank, world)
         if propagate == "auto":
             layer_bytes = graph.n_rows * d * 4
-            propagate = "replicated" if layer_bytes < (64 << 20) else ("fused" if d in (16, 32, 64, 128, 256) else "allgather")
+            propagate = "replicated" if layer_bytes < (64 << 20) else ("overlap" if d in (16, 32, 64, 128, 256) else "allgather")
         self.mode = propagate
         self.peers = None
         if self.mode == "replicated":
@@ -101,14 +104,28 @@ class ShardedEngine:
         ptr, cols, vals, self.n_local, self.new_id, self.old_of_new = shard_csr(
             e["indptr"], e["indices"], e["values"], e["row_order"], rank, world)
         del e
-        self.local = _lgx.Graph.from_csr(ptr, cols, vals, n_cols=world * self.n_local, n_users=0, m_items=0)
+        self.local = None
+        if self.mode == "overlap":
+            # row chunks of my block (contiguous in the local, degree-sorted order): one SpMM launch each
+            self.n_chunks = max(1, min(chunks, self.n_local))
+            nc = (self.n_local + self.n_chunks - 1) // self.n_chunks
+            self.chunk_rows = [(c * nc, min(self.n_local, (c + 1) * nc)) for c in range(self.n_chunks)]
+            self.chunk_rows = [(a, b) for a, b in self.chunk_rows if b > a]
+            self.chunk_graphs = []
+            for a, b in self.chunk_rows:
+                s0, s1 = int(ptr[a]), int(ptr[b])
+                self.chunk_graphs.append(_lgx.Graph.from_csr(ptr[a:b + 1] - s0, cols[s0:s1], vals[s0:s1],
+                                                             n_cols=world * self.n_local, n_users=0, m_items=0))
+            self.copy_stream = torch.cuda.Stream(device=device)
+        else:
+            self.local = _lgx.Graph.from_csr(ptr, cols, vals, n_cols=world * self.n_local, n_users=0, m_items=0)
         del ptr, cols, vals
         self.gather_src = self.old_of_new.clamp(min=0)
         self.pad_mask = (self.old_of_new < 0)
         self.has_pad = bool(self.pad_mask.any().item())
         n_tot = world * self.n_local
         self.S = torch.empty(self.n_local, d, device=device)                    # my rows of the running sum
-        if self.mode == "fused":
+        if self.mode in ("fused", "overlap"):
             self._setup_peers(n_tot, d)
             return
         self.X = [torch.zeros(n_tot, d, device=device) for _ in range(2)]       # gathered layers (ping-pong)
@@ -160,6 +177,31 @@ class ShardedEngine:
             return E0.clone()
         cur = 0
         S_in = X0[r * nl:(r + 1) * nl]
+        if self.mode == "overlap":
+            main = torch.cuda.current_stream(self.dev)
+            row_bytes = self.d * 4
+            for l in range(1, L + 1):
+                last = l == L
+                key = "mean" if last else ("x1" if cur == 0 else "x0")
+                out_full = self.full_mean if last else self.X[1 - cur]
+                for (a, b), gc in zip(self.chunk_rows, self.chunk_graphs):
+                    mine = out_full[r * nl + a: r * nl + b]                      # my rows of the gathered buffer
+                    if last:
+                        gc.spmm(self.X[cur], S_in=S_in[a:b], S_out=mine, div=float(L + 1))
+                    else:
+                        gc.spmm(self.X[cur], S_in=S_in[a:b], Y=mine, S_out=self.S[a:b])
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self.copy_stream.wait_event(ev)
+                    self._lgx.peer_copy(self.peers[key], r, (r * nl + a) * row_bytes, (b - a) * row_bytes,
+                                        self.copy_stream, self.dev)
+                done = torch.cuda.Event()
+                done.record(self.copy_stream)
+                main.wait_event(done)
+                self._layer_barrier()
+                cur = 1 - cur
+                S_in = self.S
+            return self.full_mean.index_select(0, self.new_id)
         if self.mode == "fused":
             for l in range(1, L + 1):
                 last = l == L

@@ -110,6 +110,11 @@ int lgx_spmm_peers(const lgx_graph* g, const float* X, const float* S_in, float*
 int lgx_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 int lgx_peer_open(const unsigned char* handle64, void** ptr);
 int lgx_peer_close(void* ptr);
+/* Copy-engine variant of the exchange: copy bytes [offset, offset + bytes) of this rank's buffer
+ * (peers_host[self]) into the same range of every other rank's buffer with one asynchronous P2P copy
+ * per peer on `stream` (run it on a side stream to overlap with the next chunk's SpMM). */
+int lgx_peer_copy(void* const* peers_host, int32_t n_peers, int32_t self, size_t offset_bytes, size_t bytes,
+                  lgx_stream stream);
 int lgx_peer_free(void* ptr);
 
 /* LightGCN.computer() (PT/model.py:145-177): out = mean(E0, A E0, ..., A^L E0), E0 = cat(users, items).

@@ -33,7 +33,7 @@ def _worker(rank, world, port, out_dir):
     with torch.no_grad():
         lu, li = m.computer()
         ref = torch.cat([lu, li])
-        for mode in ("fused", "replicated", "allgather"):          # every exchange variant gives the 1-GPU result
+        for mode in ("overlap", "fused", "replicated", "allgather"):          # every exchange variant gives the 1-GPU result
             eng = parallel.ShardedEngine(g, nu, mi, d, L, rank, world, dev, propagate=mode)
             assert eng.mode == mode
             for rep in range(2):                                    # twice: buffers are reused across calls
