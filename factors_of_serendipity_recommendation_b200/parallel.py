@@ -85,7 +85,8 @@ class ShardedEngine:
                        "overlap"   : every layer in `chunks` row chunks; each finished chunk is written locally and
                                      pushed to the peers by the copy engines (P2P DMA on a side stream) while the
                                      next chunk computes;
-                       "auto"      : replicated below 64 MB per layer, else overlap when d allows, else allgather."""
+                       "auto"      : replicated below 64 MB per layer, else fused when d allows, else allgather.
+        Measured on 8 B200, 1B-edge graph, 3 layers: allgather 93.1 ms, overlap 85.4 ms, fused 76.7 ms (1 GPU: 426.6)."""
         from . import _lgx
 
         self._lgx = _lgx
@@ -95,7 +96,7 @@ class ShardedEngine:
         self.lo, self.hi = item_shard_bounds(m_items, rank, world)
         if propagate == "auto":
             layer_bytes = graph.n_rows * d * 4
-            propagate = "replicated" if layer_bytes < (64 << 20) else ("overlap" if d in (16, 32, 64, 128, 256) else "allgather")
+            propagate = "replicated" if layer_bytes < (64 << 20) else ("fused" if d in (16, 32, 64, 128, 256) else "allgather")
         self.mode = propagate
         self.peers = None
         if self.mode == "replicated":
