@@ -172,9 +172,13 @@ def cpu_baseline_sample(shape, u, i, ue, ie, budget_s=20.0):
 def run_ours(args, shape):
     import torch
     import torch.distributed as dist
-    from factors_of_serendipity_recommendation_b200 import _lgx, dataloader, model, synth, world
+    from factors_of_serendipity_recommendation_b200 import build as _build
 
     rank = int(os.environ.get("RANK", "0"))
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        _build.build(verbose=False)          # no-op when liblgx.so is newer than its sources
+    from factors_of_serendipity_recommendation_b200 import _lgx, dataloader, model, synth, world
+
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world_size != args.gpus and world_size > 1:
@@ -183,6 +187,7 @@ def run_ours(args, shape):
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()                        # ranks > 0 wait for rank 0's build check
     peaks = load_peaks()
     nu, mi, E, d = shape
     mode = args.mode
