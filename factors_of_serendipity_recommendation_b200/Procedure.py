@@ -25,11 +25,22 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
     bs = world.config["bpr_batch_size"]
     total_batch = len(users) // bs + 1
     aver_loss = torch.zeros((), device=dev)
+    # config['cuda_graph']: after 3 eager steps (lazy initialisation happens there) the full-size batches
+    # replay one captured graph of the whole step; the last, shorter batch runs eagerly
+    use_graph = bool(world.config.get("cuda_graph", False)) and getattr(bpr, "fused", False) and dev.type == "cuda"
+    graphed = getattr(bpr, "_graphed", None)
     for batch_i, (bu, bp, bn) in enumerate(utils.minibatch(users, posItems, negItems, batch_size=bs)):
-        cri = bpr.stageOne(bu, bp, bn, sync=False)
+        if use_graph and len(bu) == bs and (graphed is not None or batch_i >= 3):
+            if graphed is None:
+                graphed = bpr._graphed = utils.GraphedStageOne(bpr, bu, bp, bn)
+            cri = graphed.run(bu, bp, bn)
+        else:
+            cri = bpr.stageOne(bu, bp, bn, sync=False)
         aver_loss += cri
         if world.tensorboard and w is not None:
             w.add_scalar("BPRLoss/BPR", cri.item(), epoch * int(len(users) / bs) + batch_i)
+    Recmodel._eval_cache = None
+    Recmodel._packed = {}
     aver_loss = aver_loss.item() / total_batch
     time_info = timer.dict()
     timer.zero()

@@ -56,6 +56,7 @@ _SIGS = {
     "lgx_bpr_backward_light": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
     "lgx_bpr_backward_reg": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
     "lgx_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
+    "lgx_adam_step_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "lgx_sample_bpr": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_uint64, _P, _P]),
     "lgx_rank_metrics": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
@@ -397,6 +398,13 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step: int
     with torch.cuda.device(param.device):
         check(lib().lgx_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
                                   eps, step, stream()))
+
+
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, state4):
+    require_cuda(param, grad, exp_avg, exp_avg_sq, state4)
+    with torch.cuda.device(param.device):
+        check(lib().lgx_adam_step_dev(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
+                                      eps, ptr(state4), stream()))
 
 
 def rank_metrics(topk_idx, k: int, gt_ptr, gt_items, sums3):

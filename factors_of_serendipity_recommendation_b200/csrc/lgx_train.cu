@@ -109,6 +109,32 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
   }
 }
 
+// CUDA-graph friendly Adam: the step counter lives on the device.  state = {int32 step, float step_size,
+// float bc2_sqrt, pad}; k_adam_prep advances it (bias corrections in double, like torch's host scalars).
+__global__ void k_adam_prep(int32_t* __restrict__ state, float lr, float beta1, float beta2) {
+  const int step = state[0] + 1;
+  state[0] = step;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  reinterpret_cast<float*>(state)[1] = (float)((double)lr / bc1);
+  reinterpret_cast<float*>(state)[2] = (float)sqrt(bc2);
+}
+__global__ void __launch_bounds__(256)
+k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+           float w1, float b2, float w2, const int32_t* __restrict__ state, float eps) {
+  const float step_size = __ldg(reinterpret_cast<const float*>(state) + 1);
+  const float bc2_sqrt = __ldg(reinterpret_cast<const float*>(state) + 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = fmaf(w1, gi - m[i], m[i]);
+    const float vi = fmaf(w2 * gi, gi, v[i] * b2);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = __fdiv_rn(sqrtf(vi), bc2_sqrt) + eps;
+    p[i] = p[i] - step_size * __fdiv_rn(mi, denom);
+  }
+}
+
 // splitmix64: counter-based, every (seed, sample, draw) triple gives an independent 64-bit word
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -237,6 +263,19 @@ int lgx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
   k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, 1.0f - beta1, beta2,
                                                   1.0f - beta2, step_size, bc2_sqrt, eps);
+  LGX_CHECK_LAUNCH();
+  return LGX_OK;
+}
+
+int lgx_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, int32_t* state4, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(param && grad && exp_avg && exp_avg_sq && state4, "NULL argument");
+  LGX_REQUIRE(n > 0, "n must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_adam_prep<<<1, 1, 0, st>>>(state4, lr, beta1, beta2);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
+  k_adam_dev<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, 1.0f - beta1, beta2, 1.0f - beta2, state4, eps);
   LGX_CHECK_LAUNCH();
   return LGX_OK;
 }

@@ -29,10 +29,11 @@ class BPRLoss:
                 raise RuntimeError("fused_adam needs the fused [N, d] parameter buffer (move the model to CUDA first)")
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat)
-            self._step = 0
+            self._state = torch.zeros(4, dtype=torch.int32, device=flat.device)   # device-side Adam step counter
             self.opt = None
         else:
             self.opt = optim.Adam(recmodel.parameters(), lr=self.lr)
+        self._graphed = None
 
     def stageOne(self, users, pos, neg, sync: bool = True):
         loss, reg_loss = self.model.bpr_loss(users, pos, neg)
@@ -48,8 +49,7 @@ class BPRLoss:
                 grad = torch.as_strided(gu, (flat.shape[0], flat.shape[1]), (flat.shape[1], 1))
             else:
                 grad = torch.cat([gu, gi])
-            self._step += 1
-            _lgx.adam_step(flat, grad, self._m, self._v, self.lr, 0.9, 0.999, 1e-8, self._step)
+            _lgx.adam_step_dev(flat, grad, self._m, self._v, self.lr, 0.9, 0.999, 1e-8, self._state)
             self.model._eval_cache = None
             self.model._packed = {}
         else:
@@ -57,6 +57,34 @@ class BPRLoss:
             loss.backward()
             self.opt.step()
         return loss.cpu().item() if sync else loss.detach()
+
+
+class GraphedStageOne:
+    """Whole-step CUDA graph of BPRLoss.stageOne (bpr_loss forward, backward, fused Adam) for one batch size.
+    Needs the fused Adam (no host-side step value) and no edge dropout (its seed is a host value per call).
+    Call .run(users, pos, neg) -> 0-d device tensor with the step's loss."""
+
+    def __init__(self, bpr: BPRLoss, users, pos, neg):
+        if not bpr.fused:
+            raise RuntimeError("CUDA-graph capture of the BPR step needs config['fused_adam'] = True")
+        if bpr.model.config.get("dropout") and bpr.model.training:
+            raise RuntimeError("edge dropout draws a new host-side seed per call: not graph-capturable")
+        self.bpr = bpr
+        self.u, self.p, self.n = users.clone(), pos.clone(), neg.clone()
+        side = torch.cuda.Stream(device=users.device)
+        side.wait_stream(torch.cuda.current_stream(users.device))
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                self.loss = bpr.stageOne(self.u, self.p, self.n, sync=False)
+        torch.cuda.current_stream(users.device).wait_stream(side)
+
+    def run(self, users, pos, neg):
+        self.u.copy_(users)
+        self.p.copy_(pos)
+        self.n.copy_(neg)
+        self.graph.replay()
+        return self.loss
 
 
 def UniformSample_original(dataset, neg_ratio=1, seed=None):

@@ -25,7 +25,8 @@ config = {
     "bigdata": False,
     # engine-only keys (absent from the reference)
     "score_mode": "bf16x3",       # fp32 | bf16 | bf16x3 for the fused top-K
-    "fused_adam": False,          # BPRLoss uses lgx_adam_step instead of torch.optim.Adam
+    "fused_adam": False,          # BPRLoss uses lgx_adam_step_dev instead of torch.optim.Adam
+    "cuda_graph": False,          # BPR_train_original replays one CUDA graph per full batch (needs fused_adam)
 }
 GPU = torch.cuda.is_available()
 device = torch.device("cuda" if GPU else "cpu")

@@ -204,6 +204,12 @@ int lgx_bpr_backward_reg(const float* E0, const int64_t* users, const int64_t* p
 int lgx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int32_t step, lgx_stream stream);
 
+/* Same update with the step counter on the device (state4: int32[4] = {step, step_size, bc2_sqrt, pad},
+ * zero-initialised by the caller): nothing in the call depends on a host value that changes per step,
+ * so the whole BPR step can be captured in a CUDA graph and replayed. */
+int lgx_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int32_t* state4, lgx_stream stream);
+
 /* -------------------------------------------------------------------------------------- sampler
  * BPR triples (PT/utils.py:55-99 / PT/sources/sampling.cpp:27-56), counter-based RNG on device.
  *   per_user == 0: reference Python semantics (user ~ U[0,n_users) with replacement; users without

@@ -14,6 +14,7 @@ ap.add_argument("--workload", default="yelp2018")
 ap.add_argument("--epochs", type=int, default=3)
 ap.add_argument("--fused-adam", type=int, default=1)
 ap.add_argument("--cpu-steps", type=int, default=3)
+ap.add_argument("--graph", type=int, default=1)
 args = ap.parse_args()
 
 from factors_of_serendipity_recommendation_b200 import Procedure, dataloader, model, synth, utils, world
@@ -21,7 +22,7 @@ nu, mi, E, d = synth.SHAPES[args.workload]
 u, i = synth.make_interactions(nu, mi, E, seed=2020)
 cfg = dict(world.config)
 cfg.update(lightGCN_n_layers=3, latent_dim_rec=d, fused_adam=bool(args.fused_adam))
-world.configure(bpr_batch_size=2048)
+world.configure(bpr_batch_size=2048, cuda_graph=bool(args.graph and args.fused_adam))
 ds = dataloader.InteractionDataset(nu, mi, u, i, device="cuda")
 torch.manual_seed(2020)
 m = model.LightGCN(cfg, ds).cuda()
@@ -38,7 +39,7 @@ best = min(times[1:])
 layer_bytes = g.nnz * 8 + (g.n_rows + 1) * 4 + 2 * g.n_rows * d * 4
 out = {"workload": args.workload, "steps_per_epoch": steps, "epoch_s": best, "epoch_s_all": times, "steps_per_s": steps / best,
        "ms_per_step": 1e3 * best / steps, "propagated_edges_per_s": 6 * g.nnz * steps / best,
-       "algorithmic_bytes_per_step": 6 * layer_bytes + 7 * g.n_rows * d * 4, "fused_adam": bool(args.fused_adam),
+       "algorithmic_bytes_per_step": 6 * layer_bytes + 7 * g.n_rows * d * 4, "fused_adam": bool(args.fused_adam), "cuda_graph": bool(args.graph and args.fused_adam),
        "loss_trace": infos}
 if args.cpu_steps > 0:
     from oracle import lightgcn_oracle as O

@@ -190,3 +190,24 @@ def test_model_with_dropout_trains(mlls, train_step):
         a = m.computer()[0].clone()
         b = m.computer()[0]
     assert torch.equal(a, b)                                                # eval: no dropout (PT/model.py:158-159)
+
+
+def test_cuda_graph_step_equals_eager(mlls, train_step):
+    """One captured whole-step graph replayed == the same steps run eagerly (same batches, fused Adam)."""
+    from factors_of_serendipity_recommendation_b200 import utils
+    t = train_step
+    u, p, n = batch(t)
+    outs = []
+    for graphed in (False, True):
+        m, _, cfg = make(mlls, t, fused_adam=True)
+        bpr = utils.BPRLoss(m, cfg)
+        losses = [bpr.stageOne(u, p, n, sync=False).item() for _ in range(2)]       # eager warm-up steps
+        if graphed:
+            gs = utils.GraphedStageOne(bpr, u, p, n)
+            losses += [gs.run(u.flip(0), p.flip(0), n.flip(0)).item(), gs.run(u, p, n).item()]
+        else:
+            losses += [bpr.stageOne(u.flip(0), p.flip(0), n.flip(0), sync=False).item(), bpr.stageOne(u, p, n, sync=False).item()]
+        outs.append((losses, m.embedding_user.weight.detach().clone()))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-5)
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-5
+    assert outs[0][0][3] < outs[0][0][0]
