@@ -269,7 +269,7 @@ class LightGCN(BasicModel):
             all_users, all_items = self.computer()
             users = _as_index(users, all_users.device)
             d = self.latent_dim
-            if mode_id != _lgx.SCORE_FP32 and (d % 64 != 0 or k > 64 or (mode_id == _lgx.SCORE_BF16X3 and d > 128)
+            if mode_id != _lgx.SCORE_FP32 and (d % 64 != 0 or k > 32 or (mode_id == _lgx.SCORE_BF16X3 and d > 128)
                                                or d > 256):
                 mode_id = _lgx.SCORE_FP32      # shapes the tensor-core tile does not cover run on CUDA cores
             if mode_id == _lgx.SCORE_FP32:

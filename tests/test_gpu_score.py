@@ -176,3 +176,25 @@ def test_item_sharded_merge_equals_single_pass():
             cands_v.append(pad_v)
         mi_, mv_ = _lgx.topk_merge(torch.stack(cands_i), torch.stack(cands_v))
         assert torch.equal(mi_, full_idx) and torch.equal(mv_, full_val), mode
+
+
+@pytest.mark.parametrize("k,mode", [(1, "bf16x3"), (21, "bf16x3"), (32, "bf16x3"), (33, "bf16x3"), (50, "bf16"), (100, "fp32")])
+def test_k_range(k, mode):
+    """K = 1, the register-list sizes (20 / 24 / 32) and K beyond the tensor-core path (falls back to fp32 CUDA cores)."""
+    from factors_of_serendipity_recommendation_b200 import synth
+    nu, mi, d = 150, 700, 64
+    u, i = synth.make_interactions(nu, mi, 5000, seed=k)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=k, trained_like=True)
+    m, _ = make_model(nu, mi, u, i, 2, ue.numpy(), ie.numpy(), d=d)
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=2, user_emb=ue, item_emb=ie)
+    users = np.arange(nu)
+    idx, val = m.topk(torch.from_numpy(users).cuda(), k, mode=mode)
+    tol = 1e-2 if (mode == "bf16" and k <= 32) else 1e-5
+    check_topk(reference_raw_scores(ref, users), idx.cpu().numpy(), val.cpu().numpy(), k, tol)
+    idx2, _ = m.topk(torch.from_numpy(users).cuda(), k, mode=mode, exclude_train=False)
+    s = reference_raw_scores(ref, users)
+    with torch.no_grad():
+        au, ai = ref.computer()
+    s_nomask = (au.double() @ ai.double().t()).numpy()
+    scale = np.abs(s_nomask).max()
+    assert all(O.topk_is_valid(s_nomask[r], idx2[r].cpu().numpy(), k, tol=tol * scale) for r in range(nu))
