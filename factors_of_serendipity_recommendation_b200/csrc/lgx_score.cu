@@ -168,8 +168,8 @@ k_score_topk_fp32(const float* __restrict__ U, const int64_t* __restrict__ users
   }
 }
 
-// Merge P sorted candidate lists per user into the final top-K (one warp per user; lane 0 walks the
-// P heads -- P*K is tiny).  If fewer than K unmasked items exist the tail is filled with the user's
+// Merge P sorted candidate lists per user into the final top-K (one thread per user walks the
+// P list heads -- P*K is tiny).  If fewer than K unmasked items exist the tail is filled with the user's
 // train items at -1024, which is what the reference's index_put_ + topk returns (PT/Procedure.py:134-135).
 template <typename IdxT>
 __global__ void __launch_bounds__(128)
