@@ -35,13 +35,26 @@ int score_topk_fp32(const lgx_graph* g, const float* U, const int64_t* users, in
                     int K, int64_t item_offset, int64_t* out_idx, float* out_val, void* workspace, cudaStream_t st);
 
 constexpr int TC_TILE_U = 128;                 // UMMA M
-constexpr int TC_TILE_I = 256;                 // UMMA N
 constexpr int TC_KBLK = 64;                    // bf16 elements per K-block = one 128-byte swizzle row
 constexpr int TC_A_BLOCK_BYTES = TC_TILE_U * TC_KBLK * 2;   // 16 KB
-constexpr int TC_B_STAGE_BYTES = TC_TILE_I * TC_KBLK * 2;   // 32 KB
-constexpr int TC_THREADS = 384;
-constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_TMEM_BUF = 256;               // column stride between the two accumulator buffers
+
+// Tile geometry.  NSEG = column segments per tile = epilogue warps per SM sub-partition:
+//   NSEG 2: N = 256, 8 epilogue warps, each thread owns 128 columns (4 chunks, double-buffered TMEM loads)
+//   NSEG 3: N = 192, 12 epilogue warps, each thread owns 64 columns (2 chunks) -- three warps per
+//           scheduler hide each other's TMEM-load and insert latencies; 128-register budget per thread.
+template <int NSEG>
+struct TcGeo {
+  static constexpr int TILE_I = NSEG == 2 ? 256 : 192;          // UMMA N
+  static constexpr int EPI = NSEG * TC_TILE_U;                   // epilogue threads
+  static constexpr int THREADS = 128 + EPI;
+  static constexpr int SEG_COLS = TILE_I / NSEG;
+  static constexpr int STAGE_BYTES = TILE_I * TC_KBLK * 2;      // 32 KB / 24 KB
+  // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=TILE_I, M=128.
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_I >> 3) << 17) |
+                                    ((uint32_t)(TC_TILE_U >> 4) << 24);
+};
 constexpr int TC_SMEM_LIMIT = 232448;          // 227 KB opt-in limit per CTA
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -101,9 +114,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                      // layout type: SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128.
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE_I >> 3) << 17) |
-                                ((uint32_t)(TC_TILE_U >> 4) << 24);
 
 #define LGX_TMEM_LD32(v, taddr)                                                                          \
   asm volatile(                                                                                          \
@@ -129,10 +139,17 @@ constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
                :                                                                                          \
                : "memory")
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 struct TcParams {
   int B, M, K;            // users in batch, local items, top-K
   int k_blocks, stages;   // 64-wide K blocks per tile, B-operand ring depth
   int q_cap;              // per-thread candidate queue capacity (multiple of 8)
+  int union_bound;        // row threshold from both halves' quartile ranks; the quartile array exists only then
   int n_splits, tiles_per_split;
   int64_t item_offset;
   TrainMask mask;
@@ -166,12 +183,6 @@ struct TrainCursor {
   }
 };
 
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
 // Per-thread epilogue state.
 //  * the row's top-K list lives in REGISTERS (KMAX slots, sorted best-first, right-aligned: slots
 //    [0, KMAX-K) hold +inf sentinels so the K-th best is always the last slot).  One insert is a
@@ -179,20 +190,28 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 //    no shared-memory latency (the shared-memory list version spent 30% of the epilogue there);
 //  * candidates are only APPENDED (2 stores to a shared-memory queue) inside divergent code; the 32
 //    lanes' queues are merged into the lists in a warp-convergent flush, so inserts run in lockstep.
-template <int KMAX>
+template <int KMAX, int NSEG>
 struct EpiState {
+  static constexpr int EPI = TcGeo<NSEG>::EPI;
   float lv[KMAX];
   int32_t li[KMAX];
   int qn;                       // pending candidates in the queue
-  float* qval; int32_t* qidx;   // queue, column layout [q_cap][256]
-  float* thr_mine;              // shared memory: largest float below my K-th best (published at every flush)
-  const float* thr_other;       // the same from the thread that owns the other column half of this row
+  float* qval; int32_t* qidx;   // queue, column layout [q_cap][EPI]
+  float* thr_mine;              // shared memory: largest float below my row-threshold bound (published at every flush)
+  const float* thr_other;       // the same from the thread(s) owning the other column segment(s) of this row
+  const float* thr_other2;
+  float4* quart_mine;           // NSEG 2, K == KMAX: my list's ranks K/4, K/2, 3K/4, K (published at every flush)
+  const float4* quart_other;
+  float tu;                     // what I last published to thr_mine
+  bool use_union;
   __device__ __forceinline__ float thresh() const { return lv[KMAX - 1]; }
   // Filter threshold: a score must beat my own K-th best, and must be >= the partner's K-th best -- the
   // partner already holds K items of this row at least that good, so anything below it cannot reach the
   // row's final top-K (equal scores are kept: the final merge breaks ties by item id).
   __device__ __forceinline__ float filter() const {
-    return fmaxf(lv[KMAX - 1], *reinterpret_cast<const volatile float*>(thr_other));
+    if (NSEG == 2) return max3(lv[KMAX - 1], tu, *reinterpret_cast<const volatile float*>(thr_other));
+    return max3(lv[KMAX - 1], *reinterpret_cast<const volatile float*>(thr_other),
+                *reinterpret_cast<const volatile float*>(thr_other2));
   }
   __device__ __forceinline__ void init(int K) {
 #pragma unroll
@@ -201,6 +220,7 @@ struct EpiState {
       li[p] = INT32_MAX;
     }
     qn = 0;
+    tu = -CUDART_INF_F;
   }
   // Items reach a thread in ascending id order, so an equal score always loses the tie: strict '>'.
   __device__ __forceinline__ void insert(float x, int32_t xi) {
@@ -214,12 +234,25 @@ struct EpiState {
     lv[0] = g0 ? x : lv[0];
     li[0] = g0 ? xi : li[0];
   }
+  // Row-level bound from both halves' lists (a = mine, b = partner's, ranks best-first): for any j the row
+  // already holds j + (K - j) = K items scoring >= min(a_j, b_{K-j}), so the row's final K-th best is at least
+  // max_j min(a_j, b_{K-j}) -- for two similar halves about the (K/2)-th best of each, far tighter than
+  // max(a_K, b_K).  A torn read of the partner's quartiles is harmless: every component only ever rises and
+  // each old value is itself a valid rank bound.
   __device__ __forceinline__ void flush() {
-    for (int q = 0; q < qn; q += TC_EPI_THREADS) insert(qval[q], qidx[q]);
+    for (int q = 0; q < qn; q += EPI) insert(qval[q], qidx[q]);
     qn = 0;
-    const float t = lv[KMAX - 1];                       // publish prev_float(K-th best); -inf stays -inf
-    const int tb = __float_as_int(t);
-    *thr_mine = (t == -CUDART_INF_F || t != t) ? -CUDART_INF_F : __int_as_float(tb > 0 ? tb - 1 : (tb == 0 ? (int)0x80000001 : tb + 1));
+    float t = lv[KMAX - 1];
+    if (NSEG == 2 && use_union) {
+      const float a1 = lv[KMAX / 4 - 1], a2 = lv[KMAX / 2 - 1], a3 = lv[3 * KMAX / 4 - 1];
+      const volatile float4* o = quart_other;
+      const float b1 = o->x, b2 = o->y, b3 = o->z, b4 = o->w;
+      *quart_mine = make_float4(a1, a2, a3, t);
+      t = fmaxf(max3(fminf(a1, b3), fminf(a2, b2), fminf(a3, b1)), fmaxf(t, b4));
+    }
+    const int tb = __float_as_int(t);                  // publish prev_float(bound); -inf stays -inf
+    tu = (t == -CUDART_INF_F || t != t) ? -CUDART_INF_F : __int_as_float(tb > 0 ? tb - 1 : (tb == 0 ? (int)0x80000001 : tb + 1));
+    *thr_mine = tu;
     __syncwarp();
   }
 };
@@ -228,9 +261,10 @@ struct EpiState {
 //   rare path 1: a train item of this row falls in the chunk -> its score is overwritten with -inf
 //   fast path  : max over 4 groups of 8 columns (3-input max), one compare against the threshold
 //   rare path 2: groups whose max beats the threshold append their survivors to the queue
-template <int KMAX, bool SMALLQ>
-__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KMAX>& st, int M, int q_cap,
+template <int KMAX, bool SMALLQ, int NSEG>
+__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KMAX, NSEG>& st, int M, int q_cap,
                                           TrainCursor& tc) {
+  constexpr int EPI = TcGeo<NSEG>::EPI;
   // Train items of this row inside the chunk (rare per lane, ~2%): overwrite their score with -inf.
 #ifndef LGX_EXCL_SWITCH
 #define LGX_EXCL_SWITCH 0   // A/B on B200: jump table 2.65 ms vs predicated sweep 2.38 ms (fewer instructions, but BRX divergence costs more)
@@ -286,28 +320,30 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KM
           const float s = __uint_as_float(v[i]);
           const int j = j0 + i;
           if (s > th && j < M) {
-            st.qval[st.qn] = s;               // qn counts in units of one queue row (256 entries)
+            st.qval[st.qn] = s;               // qn counts in units of one queue row (EPI entries)
             st.qidx[st.qn] = j;
-            st.qn += TC_EPI_THREADS;
+            st.qn += EPI;
           }
         }
       }
       if (SMALLQ) {                                     // small queues (big user tile in smem): check per group
         __syncwarp();
-        if (__any_sync(0xffffffffu, st.qn > (q_cap - 8) * TC_EPI_THREADS)) st.flush();
+        if (__any_sync(0xffffffffu, st.qn > (q_cap - 8) * EPI)) st.flush();
       }
     }
     if (!SMALLQ) {
       __syncwarp();
-      if (__any_sync(0xffffffffu, st.qn > (q_cap - 32) * TC_EPI_THREADS)) st.flush();   // warp-convergent
+      if (__any_sync(0xffffffffu, st.qn > (q_cap - 32) * EPI)) st.flush();   // warp-convergent
     }
   }
 }
 
-template <int KMAX, bool SMALLQ>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int KMAX, bool SMALLQ, int NSEG>
+__global__ void __launch_bounds__(TcGeo<NSEG>::THREADS, 1)
 k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_i,
                 const TcParams p) {
+  using G = TcGeo<NSEG>;
+  constexpr int EPI = G::EPI;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
@@ -315,24 +351,26 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   const uint32_t sA = base;
   const uint32_t sB = sA + (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES;
   const uint32_t off_stages = (uint32_t)p.k_blocks * TC_A_BLOCK_BYTES;
-  const uint32_t off_queue = off_stages + (uint32_t)p.stages * TC_B_STAGE_BYTES;
-  // final lists are staged over the (then idle) B-operand ring: KMAX*256*8 <= 64 KB <= 2 stages
-  float* lval_all = reinterpret_cast<float*>(gbase + off_stages);
-  int32_t* lidx_all = reinterpret_cast<int32_t*>(gbase + off_stages + (size_t)KMAX * TC_EPI_THREADS * 4);
+  const uint32_t off_queue = off_stages + (uint32_t)p.stages * G::STAGE_BYTES;
   float* qval_all = reinterpret_cast<float*>(gbase + off_queue);
-  int32_t* qidx_all = reinterpret_cast<int32_t*>(gbase + off_queue + (size_t)p.q_cap * TC_EPI_THREADS * 4);
-  const uint32_t off_bar = off_queue + (uint32_t)p.q_cap * TC_EPI_THREADS * 8;
+  int32_t* qidx_all = reinterpret_cast<int32_t*>(gbase + off_queue + (size_t)p.q_cap * EPI * 4);
+  // The final lists are staged over memory that is idle by then: the B-operand ring for NSEG 2
+  // (KMAX*256*8 <= 64 KB <= 2 stages), the thread's own (drained) queue column for NSEG 3 (q_cap >= KMAX).
+  float* lval_all = NSEG == 2 ? reinterpret_cast<float*>(gbase + off_stages) : qval_all;
+  int32_t* lidx_all = NSEG == 2 ? reinterpret_cast<int32_t*>(gbase + off_stages + (size_t)KMAX * EPI * 4) : qidx_all;
+  const uint32_t off_bar = off_queue + (uint32_t)p.q_cap * EPI * 8;
   const uint32_t bar_full = base + off_bar;                     // [stages]
   const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [stages]
   const uint32_t bar_a = bar_empty + 8 * TC_MAX_STAGES;
   const uint32_t bar_tfull = bar_a + 8;                         // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5));
-  float* thr_all = reinterpret_cast<float*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5) + 16);   // [256]
+  float* thr_all = reinterpret_cast<float*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5) + 24);   // [EPI], 16-byte aligned
+  float4* quart_all = reinterpret_cast<float4*>(gbase + off_bar + 8 * (2 * TC_MAX_STAGES + 5) + 24 + 4 * EPI);   // [EPI]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u_tile = blockIdx.x, split = blockIdx.y;
-  const int n_tiles = (p.M + TC_TILE_I - 1) / TC_TILE_I;
+  const int n_tiles = (p.M + G::TILE_I - 1) / G::TILE_I;
   const int t_begin = split * p.tiles_per_split;
   const int n_my = max(0, min(n_tiles, t_begin + p.tiles_per_split) - t_begin);
 
@@ -348,7 +386,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, TC_EPI_THREADS);
+      mbar_init(bar_tempty + 8 * b, EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -357,7 +395,10 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x < TC_EPI_THREADS) thr_all[threadIdx.x] = -CUDART_INF_F;
+  if (threadIdx.x < EPI) {
+    thr_all[threadIdx.x] = -CUDART_INF_F;
+    if (p.union_bound) quart_all[threadIdx.x] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -372,11 +413,11 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_my; ++it) {
-        const int row0 = (t_begin + it) * TC_TILE_I;
+        const int row0 = (t_begin + it) * G::TILE_I;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          mbar_expect_tx(bar_full + 8 * stage, TC_B_STAGE_BYTES);
-          tma_load_2d(sB + stage * TC_B_STAGE_BYTES, &tmap_i, bar_full + 8 * stage, kb * TC_KBLK, row0);
+          mbar_expect_tx(bar_full + 8 * stage, G::STAGE_BYTES);
+          tma_load_2d(sB + stage * G::STAGE_BYTES, &tmap_i, bar_full + 8 * stage, kb * TC_KBLK, row0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -392,15 +433,15 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         const int buf = it & 1;
         mbar_wait(bar_tempty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_TILE_I;
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_TMEM_BUF;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(sA + kb * TC_A_BLOCK_BYTES);
-          const uint64_t bdesc = umma_desc_sw128(sB + stage * TC_B_STAGE_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(sB + stage * G::STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_KBLK / 16; ++k)   // advance 16 bf16 = 32 B inside the swizzle atom: +2 in 16-byte units
-            tc_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescBf16,
+            tc_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), G::IDESC,
                        (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit(bar_empty + 8 * stage);          // frees the smem stage when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -409,62 +450,88 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (256 threads)
+    // ------------------------------------------------------------------ epilogue (EPI threads)
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int h = (warp - 4) >> 2;            // which 128-column half of the tile
+    const int h = (warp - 4) >> 2;            // which column segment of the tile
     const int row = q * 32 + lane;            // user row inside the tile == TMEM lane
     const int col = h * TC_TILE_U + row;      // this thread's list column
-    EpiState<KMAX> st;
+    EpiState<KMAX, NSEG> st;
     st.init(p.K);
     st.qval = qval_all + col; st.qidx = qidx_all + col;
-    st.thr_mine = thr_all + col; st.thr_other = thr_all + (col ^ TC_TILE_U);   // partner: same row, other half
+    st.thr_mine = thr_all + col;               // partners: same row, other segment(s)
+    st.thr_other = thr_all + ((h + 1) % NSEG) * TC_TILE_U + row;
+    st.thr_other2 = thr_all + ((h + 2) % NSEG) * TC_TILE_U + row;
+    st.quart_mine = quart_all + col;
+    st.quart_other = quart_all + ((h + 1) % NSEG) * TC_TILE_U + row;
+    st.use_union = NSEG == 2 && p.K == KMAX && p.union_bound;
     const int u = u_tile * TC_TILE_U + row;
     const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
     TrainCursor tcur;
-    tcur.init(p.mask, uid, p.item_offset, t_begin * TC_TILE_I);
+    tcur.init(p.mask, uid, p.item_offset, t_begin * G::TILE_I);
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
       mbar_wait(bar_tfull + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_TILE_I + h * 128);
-      const int j_base = (t_begin + it) * TC_TILE_I + h * 128;
-      uint32_t va[32], vb[32];
-      LGX_TMEM_LD32(va, taddr);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_TMEM_BUF + h * G::SEG_COLS);
+      const int j_base = (t_begin + it) * G::TILE_I + h * G::SEG_COLS;
+      if (NSEG == 2) {
+        uint32_t va[32], vb[32];
+        LGX_TMEM_LD32(va, taddr);
 #pragma unroll 1
-      for (int c = 0; c < 4; c += 2) {        // rolled: two chunk bodies in the instruction stream, not four
-        LGX_TMEM_WAIT(va);
-        LGX_TMEM_LD32(vb, taddr + (uint32_t)(c + 1) * 32);
-        epi_chunk<KMAX, SMALLQ>(va, j_base + c * 32, st, p.M, p.q_cap, tcur);
-        LGX_TMEM_WAIT(vb);
-        if (c == 0) {
-          LGX_TMEM_LD32(va, taddr + 64);
-        } else {
-          tc_fence_before();
-          mbar_arrive(bar_tempty + 8 * buf);  // all four chunks are in registers: TMEM buffer may be overwritten
+        for (int c = 0; c < 4; c += 2) {        // rolled: two chunk bodies in the instruction stream, not four
+          LGX_TMEM_WAIT(va);
+          LGX_TMEM_LD32(vb, taddr + (uint32_t)(c + 1) * 32);
+          epi_chunk<KMAX, SMALLQ, NSEG>(va, j_base + c * 32, st, p.M, p.q_cap, tcur);
+          LGX_TMEM_WAIT(vb);
+          if (c == 0) {
+            LGX_TMEM_LD32(va, taddr + 64);
+          } else {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * buf);  // all four chunks are in registers: TMEM buffer may be overwritten
+          }
+          epi_chunk<KMAX, SMALLQ, NSEG>(vb, j_base + (c + 1) * 32, st, p.M, p.q_cap, tcur);
         }
-        epi_chunk<KMAX, SMALLQ>(vb, j_base + (c + 1) * 32, st, p.M, p.q_cap, tcur);
+      } else {
+        // two chunks per tile, one register buffer: the other two warps of this scheduler cover the load latency
+        uint32_t va[32];
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          LGX_TMEM_LD32(va, taddr + (uint32_t)c * 32);
+          LGX_TMEM_WAIT(va);
+          if (c == 1) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * buf);
+          }
+          epi_chunk<KMAX, SMALLQ, NSEG>(va, j_base + c * 32, st, p.M, p.q_cap, tcur);
+        }
       }
     }
     st.flush();
-    // stage the register lists (the B ring is idle: every MMA of this unit has retired), merge the
-    // two column halves of every row and publish the split's partial list
+    // stage the register lists, merge the column segments of every row and publish the split's partial list
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      lval_all[k * TC_EPI_THREADS + col] = st.lv[k];
-      lidx_all[k * TC_EPI_THREADS + col] = st.li[k];
+      lval_all[k * EPI + col] = st.lv[k];
+      lidx_all[k * EPI + col] = st.li[k];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
     if (h == 0 && u < p.B) {
-      const int k0 = KMAX - p.K;                 // lists are right-aligned in their KMAX slots
-      const float* v0 = lval_all + row;  const int32_t* i0 = lidx_all + row;
-      const float* v1 = lval_all + TC_TILE_U + row;  const int32_t* i1 = lidx_all + TC_TILE_U + row;
-      int a = k0, b = k0;
+      int pos[NSEG];                              // lists are right-aligned in their KMAX slots
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) pos[s] = KMAX - p.K;
       const int64_t o = ((int64_t)split * p.B + u) * p.K;
       for (int k = 0; k < p.K; ++k) {
-        const float fa = v0[a * TC_EPI_THREADS], fb = v1[b * TC_EPI_THREADS];
-        const int32_t ia = i0[a * TC_EPI_THREADS], ib = i1[b * TC_EPI_THREADS];
-        if (better(fa, ia, fb, ib) || (fa == fb && ia == ib)) { p.ws_val[o + k] = fa; p.ws_idx[o + k] = ia; ++a; }
-        else { p.ws_val[o + k] = fb; p.ws_idx[o + k] = ib; ++b; }
+        float bv = lval_all[pos[0] * EPI + row];
+        int32_t bi = lidx_all[pos[0] * EPI + row];
+        int bs = 0;
+#pragma unroll
+        for (int s = 1; s < NSEG; ++s) {
+          const float fv = lval_all[pos[s] * EPI + s * TC_TILE_U + row];
+          const int32_t fi = lidx_all[pos[s] * EPI + s * TC_TILE_U + row];
+          if (better(fv, fi, bv, bi)) { bv = fv; bi = fi; bs = s; }
+        }
+        p.ws_val[o + k] = bv; p.ws_idx[o + k] = bi;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) pos[s] += (bs == s);
       }
     }
   }
@@ -508,27 +575,72 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int rows, int kto
   return LGX_OK;
 }
 
-struct TcConfig { int k_blocks, stages, q_cap; size_t smem; bool ok; };
+struct TcConfig { int nseg, k_blocks, stages, q_cap, tile_items, union_bound; size_t smem; bool ok; };
 
-static TcConfig tc_config(int d, int K, int mode) {
+static TcConfig tc_config_nseg(int d, int K, int mode, int nseg) {
   TcConfig c{};
+  c.nseg = nseg;
+  const int epi = nseg * TC_TILE_U;
+  const size_t stage_bytes = nseg == 2 ? TcGeo<2>::STAGE_BYTES : TcGeo<3>::STAGE_BYTES;
+  c.tile_items = nseg == 2 ? TcGeo<2>::TILE_I : TcGeo<3>::TILE_I;
   const int ktot = mode == LGX_SCORE_BF16X3 ? 3 * d : d;
-  c.ok = (d % TC_KBLK == 0) && K >= 1 && K <= 32;
+  c.ok = (d % TC_KBLK == 0) && K >= 1 && K <= (nseg == 2 ? 32 : 24);
   c.k_blocks = ktot / TC_KBLK;
+  // Queue depth vs B-ring depth, first fit: 40-row queues, else 36 rows when that buys the missing ring stage,
+  // else 16-row queues (SMALLQ kernels, no union bound: its quartile array would cost them a stage).
+  static const int forced_q = [] { const char* e = std::getenv("LGX_SCORE_QCAP"); return e ? std::atoi(e) : 0; }();
+  static const int union_env = [] { const char* e = std::getenv("LGX_SCORE_UNION"); return e ? std::atoi(e) : 1; }();
+  const int want = c.k_blocks == 1 ? 4 : 3;
+  const int cands[3] = {40, 36, 16};
   size_t fixed = 0;
-  for (c.q_cap = 40; c.q_cap >= 16; c.q_cap -= 24) {    // shrink the candidate queues before giving up stages
-    fixed = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)c.q_cap * TC_EPI_THREADS * 8 +
-            8 * (2 * TC_MAX_STAGES + 5) + 16 + 4 * TC_EPI_THREADS;
-    if (fixed + 3 * (size_t)TC_B_STAGE_BYTES <= TC_SMEM_LIMIT) break;
+  bool found = false;
+  for (int i = 0; i < 3 && !found; ++i) {
+    const int qc = cands[i];
+    if (forced_q && qc != forced_q) continue;              // LGX_SCORE_QCAP=40|36|16: A/B runs
+    if (nseg == 3 && qc < 40) continue;                    // the 12-warp variant stages its lists over full-size queues
+    const int uni = (qc >= 36 && nseg == 2 && union_env) ? 1 : 0;
+    const size_t fx = 1024 + (size_t)c.k_blocks * TC_A_BLOCK_BYTES + (size_t)qc * epi * 8 +
+                      8 * (2 * TC_MAX_STAGES + 5) + 24 + (size_t)(4 + 16 * uni) * epi;
+    const int need = (qc == 16 || forced_q || nseg == 3) ? 2 : want;
+    if (fx + (size_t)need * stage_bytes > TC_SMEM_LIMIT) continue;
+    c.q_cap = qc; c.union_bound = uni; fixed = fx; found = true;
+    c.stages = (int)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_LIMIT - fx) / stage_bytes);
   }
-  if (c.q_cap < 16) c.q_cap = 16;
-  if (!c.ok || fixed + 2 * (size_t)TC_B_STAGE_BYTES > TC_SMEM_LIMIT) { c.ok = false; return c; }
-  c.stages = (int)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / TC_B_STAGE_BYTES);
-  c.smem = fixed + (size_t)c.stages * TC_B_STAGE_BYTES;
+  if (!c.ok || !found) { c.ok = false; return c; }
+  c.smem = fixed + (size_t)c.stages * stage_bytes;
   return c;
 }
 
-static ScorePlan tc_plan(int B, int M) { return plan_score(B, M, TC_TILE_U, TC_TILE_I, sm_count(), 1); }
+// Default: 8 epilogue warps over 256-column tiles.  LGX_SCORE_NSEG=3 selects the 12-warp / 192-column variant
+// where it fits (k <= 24, full-size queues + >= 2 stages: d = 64, bf16 d = 128).  Measured on B200 at the
+// Amazon-Book shape it is 2% SLOWER (2.42 vs 2.37 ms): a third list per row adds inserts and the single
+// TMEM register buffer exposes load latency, which cancels the extra latency hiding -- kept for A/B runs.
+static TcConfig tc_config(int d, int K, int mode) {
+  static const int forced = [] { const char* e = std::getenv("LGX_SCORE_NSEG"); return e ? std::atoi(e) : 0; }();
+  if (forced == 3) {
+    const TcConfig c3 = tc_config_nseg(d, K, mode, 3);
+    if (c3.ok) return c3;
+  }
+  return tc_config_nseg(d, K, mode, 2);
+}
+
+static ScorePlan tc_plan(int B, int M, const TcConfig& cfg) {
+  return plan_score(B, M, TC_TILE_U, cfg.tile_items, sm_count(), 1);
+}
+
+template <int KMAX, bool SMALLQ, int NSEG>
+static int launch_tc(dim3 grid, const TcConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
+                     const TcParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<KMAX, SMALLQ, NSEG>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    configured = true;
+  }
+  k_score_topk_tc<KMAX, SMALLQ, NSEG><<<grid, TcGeo<NSEG>::THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  LGX_CHECK_LAUNCH();
+  return LGX_OK;
+}
 
 static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* users, int B, const void* I_op, int M,
                          int d, int K, int mode, int64_t item_offset, int64_t* out_idx, float* out_val,
@@ -543,32 +655,27 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   CUtensorMap tm_u, tm_i;
   int rc = make_operand_map(&tm_u, U_op, B, ktot, TC_TILE_U);
   if (rc != LGX_OK) return rc;
-  rc = make_operand_map(&tm_i, I_op, M, ktot, TC_TILE_I);
+  rc = make_operand_map(&tm_i, I_op, M, ktot, cfg.tile_items);
   if (rc != LGX_OK) return rc;
-  const ScorePlan plan = tc_plan(B, M);
+  const ScorePlan plan = tc_plan(B, M, cfg);
   TcParams p;
   p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages; p.q_cap = cfg.q_cap;
   p.n_splits = plan.n_splits; p.tiles_per_split = plan.tiles_per_split; p.item_offset = item_offset;
   p.mask = make_mask(g); p.users = users;
+  p.union_bound = cfg.union_bound;
   p.ws_val = reinterpret_cast<float*>(workspace);
   p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
-  static bool configured = false;
-  if (!configured) {
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    configured = true;
-  }
   dim3 grid(plan.n_user_tiles, plan.n_splits);
-  const bool smallq = cfg.q_cap < 40;
-  if (K <= 20 && !smallq) k_score_topk_tc<20, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);   // the reference's default topks=[20]
-  else if (K <= 24 && !smallq) k_score_topk_tc<24, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
-  else if (K <= 24) k_score_topk_tc<24, true><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
-  else if (!smallq) k_score_topk_tc<32, false><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
-  else k_score_topk_tc<32, true><<<grid, TC_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
-  LGX_CHECK_LAUNCH();
+  const bool smallq = cfg.q_cap < 36;
+  if (cfg.nseg == 3) {
+    if (K <= 20) rc = launch_tc<20, false, 3>(grid, cfg, tm_u, tm_i, p, st);   // the reference's default topks=[20]
+    else rc = launch_tc<24, false, 3>(grid, cfg, tm_u, tm_i, p, st);
+  } else if (K <= 20 && !smallq) rc = launch_tc<20, false, 2>(grid, cfg, tm_u, tm_i, p, st);
+  else if (K <= 24 && !smallq) rc = launch_tc<24, false, 2>(grid, cfg, tm_u, tm_i, p, st);
+  else if (K <= 24) rc = launch_tc<24, true, 2>(grid, cfg, tm_u, tm_i, p, st);
+  else if (!smallq) rc = launch_tc<32, false, 2>(grid, cfg, tm_u, tm_i, p, st);
+  else rc = launch_tc<32, true, 2>(grid, cfg, tm_u, tm_i, p, st);
+  if (rc != LGX_OK) return rc;
   return launch_merge_i32(p.ws_val, p.ws_idx, plan.n_splits, B, K, item_offset, M, p.mask, users, out_idx, out_val, st);
 }
 
@@ -580,12 +687,16 @@ extern "C" {
 
 size_t lgx_score_topk_workspace_bytes(int32_t B, int32_t M, int32_t d, int32_t k, int32_t mode) {
   if (B <= 0 || M <= 0 || k <= 0) return 0;
-  (void)d;
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) sms = sm_count(); else cudaGetLastError();
+  int tile_items = 64;
+  if (mode != LGX_SCORE_FP32) {
+    const TcConfig cfg = tc_config(d, k, mode);
+    tile_items = cfg.ok ? cfg.tile_items : TcGeo<2>::TILE_I;
+  }
   const ScorePlan plan = mode == LGX_SCORE_FP32 ? plan_score(B, M, 64, 64, sms, 4)
-                                                : plan_score(B, M, TC_TILE_U, TC_TILE_I, sms, 1);
+                                                : plan_score(B, M, TC_TILE_U, tile_items, sms, 1);
   return (size_t)plan.n_splits * B * k * 8 + 256;
 }
 

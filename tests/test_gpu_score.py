@@ -198,3 +198,35 @@ def test_k_range(k, mode):
     s_nomask = (au.double() @ ai.double().t()).numpy()
     scale = np.abs(s_nomask).max()
     assert all(O.topk_is_valid(s_nomask[r], idx2[r].cpu().numpy(), k, tol=tol * scale) for r in range(nu))
+
+
+def test_twelve_warp_variant_matches_default():
+    """LGX_SCORE_NSEG=3 (192-column tiles, 12 epilogue warps; opt-in A/B variant) returns the same top-K as the
+    default kernel.  The switch is read once per process, so the variant runs in a child interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch
+from factors_of_serendipity_recommendation_b200 import _lgx
+g = torch.Generator().manual_seed(5)
+B, M, d = 300, 3 * 192 + 50, 64
+U = torch.randn(B, d, generator=g).cuda(); I = torch.randn(M, d, generator=g).cuda()
+out = {}
+Up = _lgx.pack_operand(U, None, _lgx.SCORE_BF16, False); Ip = _lgx.pack_operand(I, None, _lgx.SCORE_BF16, True)
+for k in (20, 24):
+    idx, val = _lgx.score_topk(None, Up, None, Ip, d, k, _lgx.SCORE_BF16)
+    out[f"i{k}"] = idx.cpu().numpy(); out[f"v{k}"] = val.cpu().numpy()
+np.savez(__import__("sys").argv[1], **out)
+"""
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for nseg in ("2", "3"):
+            path = os.path.join(tmp, f"o{nseg}.npz")
+            env = dict(os.environ, LGX_SCORE_NSEG=nseg)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            res[nseg] = dict(np.load(path))
+    for key in res["2"]:
+        assert np.array_equal(res["2"][key], res["3"][key]), key
