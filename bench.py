@@ -312,13 +312,13 @@ def run_ours(args, shape):
             pipe = serving.HostPipeline.for_model(m, all_users, K_TOP, mode=mode, depth=args.e2e_depth, flush_l2=flush)
         host_outs = [host_out] + [torch.empty_like(host_out).pin_memory() for _ in range(args.e2e_depth)]
 
-        for i in range(3):
-            pipe.submit(host_u, host_i, host_outs[i % len(host_outs)])
+        for step_no in range(3):
+            pipe.submit(host_u, host_i, host_outs[step_no % len(host_outs)])
         pipe.wait()
         barrier()
         t_a = pipe.start_event()
-        for i in range(args.steps):
-            pipe.submit(host_u, host_i, host_outs[i % len(host_outs)])
+        for step_no in range(args.steps):
+            pipe.submit(host_u, host_i, host_outs[step_no % len(host_outs)])
         t_b = pipe.last_download
         pipe.wait()
         barrier()

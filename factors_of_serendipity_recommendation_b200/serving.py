@@ -38,8 +38,10 @@ class HostPipeline:
         self.s_down = torch.cuda.Stream(device=self.dev)
         for st in (self.s_up, self.s_comp, self.s_down):   # whatever the caller prepared on its stream is visible
             st.wait_stream(torch.cuda.current_stream(self.dev))
+        self.idx = [None] * depth               # per-slot [B, k] result buffers, allocated by the first request
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
         self.computed = [None] * depth          # recorded once the slot has been used
+        self.downloaded = [None] * depth
         self.n_submitted = 0
         self.last_download = None
 
@@ -92,16 +94,25 @@ class HostPipeline:
             self.uploaded[b].record(self.s_up)
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(self.uploaded[b])
+            if self.downloaded[b] is not None:
+                self.s_comp.wait_event(self.downloaded[b])    # the slot's previous result has left the device
             if self.flush_l2 is not None:
                 self.flush_l2.fill_(1)                        # benchmarking: evict L2 between requests
             idx, _ = self.step_fn(tables, self.light[b])
+            # Results leave through a per-slot buffer: every temporary of the step lives and dies on the compute
+            # stream, so the caching allocator reuses it in stream order however far the host runs ahead (a
+            # cross-stream record_stream() lifetime forced fresh cudaMallocs -- sporadic 3x stalls on B200).
+            if self.idx[b] is None or self.idx[b].shape != idx.shape:
+                self.idx[b] = torch.empty_like(idx)
+            self.idx[b].copy_(idx)
             done = torch.cuda.Event()
             done.record(self.s_comp)
             self.computed[b] = done
-        idx.record_stream(self.s_down)
         with torch.cuda.stream(self.s_down):
             self.s_down.wait_event(done)
-            host_out.copy_(idx, non_blocking=True)
+            host_out.copy_(self.idx[b], non_blocking=True)
+            self.downloaded[b] = torch.cuda.Event()
+            self.downloaded[b].record(self.s_down)
             self.last_download = torch.cuda.Event(enable_timing=True)
             self.last_download.record(self.s_down)
         self.n_submitted += 1
