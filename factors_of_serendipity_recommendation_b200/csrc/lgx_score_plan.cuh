@@ -35,4 +35,29 @@ inline ScorePlan plan_score(int B, int M, int tile_users, int tile_items, int sm
   return p;
 }
 
+// Wave-aware variant for the tcgen05 kernel, whose CTAs share every row's running bound through global memory
+// (TcParams::row_bound): a split no longer restarts the threshold from scratch, so splits are cheap enough to be
+// used for making units / SMs nearly integral.  Cost model (tile units): waves(R) * (item_tiles / R + c0), with
+// c0 = the measured per-unit overhead (A tile reload, pipeline fill, list staging, the unit's early inserts)
+// ~ 14 item tiles: on B200 the Amazon-Book pass (412 user tiles x 358 item tiles) takes 2.15 / 2.29 / 2.32 / 2.41 /
+// 2.74 ms with R = 1 / 4 / 5 / 6 / 10, so it stays unsplit; a 4096-user batch x 250 K items (32 user tiles) went
+// from 5 splits = 160 units = 2 waves at 54 % (0.74 ms) to R = 9 = 1.95 waves (0.50 ms).
+inline ScorePlan plan_score_waves(int B, int M, int tile_users, int tile_items, int sms, double unit_overhead_tiles) {
+  ScorePlan p;
+  p.n_user_tiles = (B + tile_users - 1) / tile_users;
+  p.n_item_tiles = (M + tile_items - 1) / tile_items;
+  const int max_r = std::max(1, std::min(std::min(p.n_item_tiles / 8, kMaxSplits), 64));
+  int best_r = 1;
+  double best_cost = 1e300;
+  for (int r = 1; r <= max_r; ++r) {
+    const long units = (long)r * p.n_user_tiles;
+    const long waves = (units + sms - 1) / sms;
+    const double cost = (double)waves * ((double)p.n_item_tiles / r + unit_overhead_tiles);
+    if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best_r = r; }
+  }
+  p.tiles_per_split = (p.n_item_tiles + best_r - 1) / best_r;
+  p.n_splits = (p.n_item_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  return p;
+}
+
 }  // namespace lgx

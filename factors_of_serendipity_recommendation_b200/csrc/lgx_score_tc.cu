@@ -164,7 +164,18 @@ struct TcParams {
   const int64_t* users;   // global user id per batch row (mask lookup) or NULL
   float* ws_val;          // [n_splits, B, K]
   int32_t* ws_idx;
+  unsigned* row_bound;    // [B] ordered-uint encoding of each row's best known lower bound on its final K-th
+                          // score, shared by every CTA that works on the row (NULL when n_splits == 1)
 };
+
+// float <-> unsigned with the same ordering (for atomicMax); 0 sorts below every float
+__device__ __forceinline__ unsigned ord_encode(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_decode(unsigned u) {
+  return u == 0u ? -CUDART_INF_F : __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
 
 // Monotone cursor over one user's sorted train-item list (the user row of the bipartite CSR).
 // Item tiles are visited in ascending order, so "is this column a train item" is a compare against
@@ -198,7 +209,7 @@ struct TrainCursor {
 //    no shared-memory latency (the shared-memory list version spent 30% of the epilogue there);
 //  * candidates are only APPENDED (2 stores to a shared-memory queue) inside divergent code; the 32
 //    lanes' queues are merged into the lists in a warp-convergent flush, so inserts run in lockstep.
-template <int KMAX, int NSEG>
+template <int KMAX, int NSEG, bool SHARE>
 struct EpiState {
   static constexpr int EPI = TcGeo<NSEG>::EPI;
   float lv[KMAX];
@@ -213,6 +224,7 @@ struct EpiState {
   const float4* quart_other;
   float tu;                     // what I last published to thr_mine
   bool use_union;
+  unsigned* gbound;             // this row's slot of TcParams::row_bound, or NULL
   __device__ __forceinline__ float thresh() const { return lv[KMAX - 1]; }
   // Filter threshold: a score must beat my own K-th best, and must be >= the partner's K-th best -- the
   // partner already holds K items of this row at least that good, so anything below it cannot reach the
@@ -255,6 +267,8 @@ struct EpiState {
   // max(a_K, b_K).  A torn read of the partner's quartiles is harmless: every component only ever rises and
   // each old value is itself a valid rank bound.
   __device__ __forceinline__ void flush() {
+    // other CTAs' bound for this row: loaded first, consumed after the inserts
+    const unsigned gb = (SHARE && gbound) ? *reinterpret_cast<const volatile unsigned*>(gbound) : 0u;
     for (const float* a = qbase; a < qhead; a += ROW) insert(a[0], reinterpret_cast<const int32_t*>(a)[EPI]);
     qhead = qbase;
     float t = lv[KMAX - 1];
@@ -264,6 +278,11 @@ struct EpiState {
       const float b1 = o->x, b2 = o->y, b3 = o->z, b4 = o->w;
       *quart_mine = make_float4(a1, a2, a3, t);
       t = fmaxf(max3(fminf(a1, b3), fminf(a2, b2), fminf(a3, b1)), fmaxf(t, b4));
+    }
+    if (SHARE && gbound) {
+      const unsigned mine = (t != t) ? 0u : ord_encode(t);
+      if (mine > gb) atomicMax(gbound, mine);
+      t = fmaxf(t, ord_decode(gb));
     }
     const int tb = __float_as_int(t);                  // publish prev_float(bound); -inf stays -inf
     tu = (t == -CUDART_INF_F || t != t) ? -CUDART_INF_F : __int_as_float(tb > 0 ? tb - 1 : (tb == 0 ? (int)0x80000001 : tb + 1));
@@ -276,8 +295,8 @@ struct EpiState {
 //   rare path 1: a train item of this row falls in the chunk -> its score is overwritten with -inf
 //   fast path  : max over 4 groups of 8 columns (3-input max), one compare against the threshold
 //   rare path 2: groups whose max beats the threshold append their survivors to the queue
-template <int KMAX, bool SMALLQ, int NSEG>
-__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KMAX, NSEG>& st, int q_cap,
+template <int KMAX, bool SMALLQ, int NSEG, bool SHARE>
+__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KMAX, NSEG, SHARE>& st, int q_cap,
                                           TrainCursor& tc) {
   // Train items of this row inside the chunk (rare per lane, ~2%): overwrite their score with -inf.
   if (tc.next < j0 + 32) {
@@ -332,7 +351,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], int j0, EpiState<KM
   }
 }
 
-template <int KMAX, bool SMALLQ, int NSEG>
+template <int KMAX, bool SMALLQ, int NSEG, bool SHARE>
 __global__ void __launch_bounds__(TcGeo<NSEG>::THREADS, 1)
 k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_i,
                 const TcParams p) {
@@ -448,7 +467,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     const int h = (warp - 4) >> 2;            // which column segment of the tile
     const int row = q * 32 + lane;            // user row inside the tile == TMEM lane
     const int col = h * TC_TILE_U + row;      // this thread's list column
-    EpiState<KMAX, NSEG> st;
+    EpiState<KMAX, NSEG, SHARE> st;
     st.init(p.K);
     st.qbase = st.qhead = reinterpret_cast<float*>(gbase + off_queue) + col;
     st.thr_mine = thr_all + col;               // partners: same row, other segment(s)
@@ -457,6 +476,8 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     st.quart_mine = quart_all + col;
     st.quart_other = quart_all + ((h + 1) % NSEG) * TC_TILE_U + row;
     st.use_union = NSEG == 2 && p.K == KMAX && p.union_bound;
+    st.gbound = (SHARE && u_tile * TC_TILE_U + row < p.B) ? p.row_bound + (u_tile * TC_TILE_U + row) : nullptr;
+    if (SHARE) st.flush();                     // start from what earlier / concurrent units of this row already know
     const int u = u_tile * TC_TILE_U + row;
     const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
     TrainCursor tcur;
@@ -474,7 +495,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         for (int c = 0; c < 4; c += 2) {        // rolled: two chunk bodies in the instruction stream, not four
           LGX_TMEM_WAIT(va);
           LGX_TMEM_LD32(vb, taddr + (uint32_t)(c + 1) * 32);
-          epi_chunk<KMAX, SMALLQ, NSEG>(va, j_base + c * 32, st, p.q_cap, tcur);
+          epi_chunk<KMAX, SMALLQ, NSEG, SHARE>(va, j_base + c * 32, st, p.q_cap, tcur);
           LGX_TMEM_WAIT(vb);
           if (c == 0) {
             LGX_TMEM_LD32(va, taddr + 64);
@@ -482,7 +503,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * buf);  // all four chunks are in registers: TMEM buffer may be overwritten
           }
-          epi_chunk<KMAX, SMALLQ, NSEG>(vb, j_base + (c + 1) * 32, st, p.q_cap, tcur);
+          epi_chunk<KMAX, SMALLQ, NSEG, SHARE>(vb, j_base + (c + 1) * 32, st, p.q_cap, tcur);
         }
       } else {
         // two chunks per tile, one register buffer: the other two warps of this scheduler cover the load latency
@@ -495,7 +516,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * buf);
           }
-          epi_chunk<KMAX, SMALLQ, NSEG>(va, j_base + c * 32, st, p.q_cap, tcur);
+          epi_chunk<KMAX, SMALLQ, NSEG, SHARE>(va, j_base + c * 32, st, p.q_cap, tcur);
         }
       }
     }
@@ -618,22 +639,41 @@ static TcConfig tc_config(int d, int K, int mode) {
   return tc_config_nseg(d, K, mode, 2);
 }
 
-static ScorePlan tc_plan(int B, int M, const TcConfig& cfg) {
-  return plan_score(B, M, TC_TILE_U, cfg.tile_items, sm_count(), 1);
+// Splits per user tile: wave-aware (lgx_score_plan.cuh).  LGX_SCORE_SPLITS=R forces R (A/B runs),
+// LGX_SCORE_UNIT_OVERHEAD sets the chooser's per-unit overhead in item tiles of 256 columns.
+static ScorePlan tc_plan(int B, int M, const TcConfig& cfg, int sms) {
+  static const int forced = [] { const char* e = std::getenv("LGX_SCORE_SPLITS"); return e ? std::atoi(e) : 0; }();
+  static const double c0 = [] { const char* e = std::getenv("LGX_SCORE_UNIT_OVERHEAD"); return e ? std::atof(e) : 14.0; }();
+  ScorePlan p = plan_score_waves(B, M, TC_TILE_U, cfg.tile_items, sms, c0 * 256.0 / cfg.tile_items);
+  if (forced > 0) {
+    const int r = std::max(1, std::min(forced, std::min(p.n_item_tiles, kMaxSplits)));
+    p.tiles_per_split = (p.n_item_tiles + r - 1) / r;
+    p.n_splits = (p.n_item_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  }
+  return p;
 }
 
-template <int KMAX, bool SMALLQ, int NSEG>
-static int launch_tc(dim3 grid, const TcConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
+template <int KMAX, bool SMALLQ, int NSEG, bool SHARE>
+static int launch_tc2(dim3 grid, const TcConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
                      const TcParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<KMAX, SMALLQ, NSEG>,
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<KMAX, SMALLQ, NSEG, SHARE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     configured = true;
   }
-  k_score_topk_tc<KMAX, SMALLQ, NSEG><<<grid, TcGeo<NSEG>::THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  k_score_topk_tc<KMAX, SMALLQ, NSEG, SHARE><<<grid, TcGeo<NSEG>::THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
   LGX_CHECK_LAUNCH();
   return LGX_OK;
+}
+
+// SHARE (rows' bounds exchanged through TcParams::row_bound) is compiled in only when a row is split over several
+// CTAs: carried unused it cost the single-split Amazon-Book pass 4 % (2.06 -> 2.15 ms).
+template <int KMAX, bool SMALLQ, int NSEG>
+static int launch_tc(dim3 grid, const TcConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
+                     const TcParams& p, cudaStream_t st) {
+  return p.row_bound ? launch_tc2<KMAX, SMALLQ, NSEG, true>(grid, cfg, tm_u, tm_i, p, st)
+                     : launch_tc2<KMAX, SMALLQ, NSEG, false>(grid, cfg, tm_u, tm_i, p, st);
 }
 
 static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* users, int B, const void* I_op, int M,
@@ -651,7 +691,7 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   if (rc != LGX_OK) return rc;
   rc = make_operand_map(&tm_i, I_op, M, ktot, cfg.tile_items);
   if (rc != LGX_OK) return rc;
-  const ScorePlan plan = tc_plan(B, M, cfg);
+  const ScorePlan plan = tc_plan(B, M, cfg, sm_count());
   TcParams p;
   p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages; p.q_cap = cfg.q_cap;
   p.n_splits = plan.n_splits; p.tiles_per_split = plan.tiles_per_split; p.item_offset = item_offset;
@@ -659,6 +699,11 @@ static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* us
   p.union_bound = cfg.union_bound;
   p.ws_val = reinterpret_cast<float*>(workspace);
   p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
+  p.row_bound = nullptr;
+  if (plan.n_splits > 1) {                      // rows are worked on by several CTAs: share their bounds
+    p.row_bound = reinterpret_cast<unsigned*>(p.ws_idx + (size_t)plan.n_splits * B * K);
+    LGX_CHECK_CUDA(cudaMemsetAsync(p.row_bound, 0, (size_t)B * sizeof(unsigned), st));
+  }
   dim3 grid(plan.n_user_tiles, plan.n_splits);
   const bool smallq = cfg.q_cap < 36;
   if (cfg.nseg == 3) {
@@ -684,14 +729,11 @@ size_t lgx_score_topk_workspace_bytes(int32_t B, int32_t M, int32_t d, int32_t k
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) sms = sm_count(); else cudaGetLastError();
-  int tile_items = 64;
-  if (mode != LGX_SCORE_FP32) {
-    const TcConfig cfg = tc_config(d, k, mode);
-    tile_items = cfg.ok ? cfg.tile_items : TcGeo<2>::TILE_I;
-  }
-  const ScorePlan plan = mode == LGX_SCORE_FP32 ? plan_score(B, M, 64, 64, sms, 4)
-                                                : plan_score(B, M, TC_TILE_U, tile_items, sms, 1);
-  return (size_t)plan.n_splits * B * k * 8 + 256;
+  if (mode == LGX_SCORE_FP32) return (size_t)plan_score(B, M, 64, 64, sms, 4).n_splits * B * k * 8 + 256;
+  TcConfig cfg = tc_config(d, k, mode);
+  if (!cfg.ok) cfg.tile_items = TcGeo<2>::TILE_I;
+  const ScorePlan plan = tc_plan(B, M, cfg, sms);
+  return (size_t)plan.n_splits * B * k * 8 + (size_t)B * sizeof(unsigned) + 256;
 }
 
 int lgx_score_topk(const lgx_graph* g, const void* U_op, const int64_t* users, int32_t B, const void* I_op, int32_t M,
