@@ -306,8 +306,9 @@ def run_ours(args, shape):
         # overlap their copies with the neighbours' kernels (depth-2 device slots).
         from factors_of_serendipity_recommendation_b200 import serving
         if engine is not None:
+            up_group = dist.new_group(backend="nccl") if args.e2e_upload == "sharded" else None
             pipe = serving.HostPipeline.for_engine(engine, N, d, all_users, K_TOP, mode_id, shard=args.shard,
-                                                   depth=args.e2e_depth, flush_l2=flush)
+                                                   depth=args.e2e_depth, flush_l2=flush, upload_group=up_group)
         else:
             pipe = serving.HostPipeline.for_model(m, all_users, K_TOP, mode=mode, depth=args.e2e_depth, flush_l2=flush)
         host_outs = [host_out] + [torch.empty_like(host_out).pin_memory() for _ in range(args.e2e_depth)]
@@ -371,7 +372,8 @@ def run_ours(args, shape):
                     "d2h_bytes_per_step": int(n_score * K_TOP * 8),
                     "ms_per_step": e2e_total / args.steps if e2e_total else None,
                     "api": "serving.HostPipeline.submit(host_user_emb, host_item_emb, host_out)",
-                    "pipeline_depth": args.e2e_depth, "l2_flush_inside": True},
+                    "pipeline_depth": args.e2e_depth, "l2_flush_inside": True,
+                    "upload": (args.e2e_upload if world_size > 1 else "full")},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -392,6 +394,9 @@ def main():
     ap.add_argument("--workload", default="amazon-book")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-upload", default="sharded", choices=["sharded", "full"],
+                    help="N > 1: each rank uploads 1/N of the table rows and the ranks all-gather over NVLink (sharded), "
+                         "or every rank uploads the whole tables over its own PCIe link (full)")
     ap.add_argument("--e2e-depth", type=int, default=2,
                     help="device slots of the host pipeline in the e2e leg (1 = copies and kernels strictly serial)")
     ap.add_argument("--propagate", default="auto", choices=["auto", "overlap", "fused", "allgather", "replicated"],

@@ -24,14 +24,32 @@ class HostPipeline:
     LightGCN model on one GPU, ``for_engine`` for a ``parallel.ShardedEngine`` rank.
     """
 
-    def __init__(self, step_fn, n_rows: int, dim: int, device, depth: int = 2, flush_l2: torch.Tensor | None = None):
+    def __init__(self, step_fn, n_rows: int, dim: int, device, depth: int = 2, flush_l2: torch.Tensor | None = None,
+                 upload_group=None):
+        """``upload_group``: a torch.distributed process group used ONLY for uploads.  With it every rank copies
+        1/world of the table rows from the host and the ranks all-gather them over NVLink, instead of each rank
+        pulling the whole table over its own PCIe link (at 8 GPUs the full upload, not the kernels, bounded the
+        step).  It must be a dedicated group: collectives of one group are serialised in issue order, so sharing
+        the compute path's group would chain request i+1's upload behind request i's kernels."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.step_fn = step_fn
         self.dev = torch.device(device)
         self.depth = depth
         self.flush_l2 = flush_l2
-        self.tables = [torch.empty(n_rows, dim, dtype=torch.float32, device=self.dev) for _ in range(depth)]
+        self.n_rows = n_rows
+        self.group = upload_group
+        if upload_group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(upload_group), dist.get_rank(upload_group)
+            self.chunk = (n_rows + self.world - 1) // self.world
+            self.padded = [torch.empty(self.chunk * self.world, dim, dtype=torch.float32, device=self.dev)
+                           for _ in range(depth)]
+            self.local = [torch.empty(self.chunk, dim, dtype=torch.float32, device=self.dev) for _ in range(depth)]
+            self.tables = [t[:n_rows] for t in self.padded]
+        else:
+            self.world, self.rank = 1, 0
+            self.tables = [torch.empty(n_rows, dim, dtype=torch.float32, device=self.dev) for _ in range(depth)]
         self.light = [torch.empty(n_rows, dim, dtype=torch.float32, device=self.dev) for _ in range(depth)]
         self.s_up = torch.cuda.Stream(device=self.dev)
         self.s_comp = torch.cuda.Stream(device=self.dev)
@@ -67,11 +85,11 @@ class HostPipeline:
 
     @classmethod
     def for_engine(cls, engine, n_rows: int, dim: int, users, k: int, mode_id: int, shard: str = "auto", depth: int = 2,
-                   flush_l2=None):
+                   flush_l2=None, upload_group=None):
         def step(E0, light):
             return engine.step(E0, users, k, mode_id, shard=shard)
 
-        return cls(step, n_rows, dim, engine.dev, depth=depth, flush_l2=flush_l2)
+        return cls(step, n_rows, dim, engine.dev, depth=depth, flush_l2=flush_l2, upload_group=upload_group)
 
     # ---- one request
     def submit(self, host_user: torch.Tensor, host_item: torch.Tensor, host_out: torch.Tensor) -> None:
@@ -89,8 +107,19 @@ class HostPipeline:
         with torch.cuda.stream(self.s_up):
             if self.computed[b] is not None:
                 self.s_up.wait_event(self.computed[b])        # the slot's previous request has consumed its tables
-            tables[:nu].copy_(host_user, non_blocking=True)
-            tables[nu:].copy_(host_item, non_blocking=True)
+            if self.group is None:
+                tables[:nu].copy_(host_user, non_blocking=True)
+                tables[nu:].copy_(host_item, non_blocking=True)
+            else:
+                import torch.distributed as dist
+                r0 = self.rank * self.chunk                      # my rows [r0, r1) of the stacked [users; items] table
+                r1 = min(self.n_rows, r0 + self.chunk)
+                local = self.local[b]
+                if r0 < min(r1, nu):
+                    local[:min(r1, nu) - r0].copy_(host_user[r0:min(r1, nu)], non_blocking=True)
+                if max(r0, nu) < r1:
+                    local[max(r0, nu) - r0:r1 - r0].copy_(host_item[max(r0, nu) - nu:r1 - nu], non_blocking=True)
+                dist.all_gather_into_tensor(self.padded[b], local, group=self.group)
             self.uploaded[b].record(self.s_up)
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(self.uploaded[b])

@@ -49,6 +49,21 @@ def _worker(rank, world, port, out_dir):
         idx, val = eng.step(E0, users, k, _lgx.MODES["bf16x3"])
         same = (idx == m.topk(users, k, mode="bf16x3")[0]).float().mean().item()
         assert same > 0.999                                               # propagate differs in the last ulp only
+        # host pipeline over the engine: sharded upload (1/world of the rows per rank + all-gather on a dedicated
+        # group) and full upload return the same ids for every request, in order
+        from factors_of_serendipity_recommendation_b200 import serving
+        reqs = [tuple(t.pin_memory() for t in synth.make_embeddings(nu, mi, d, seed=s, trained_like=True)) for s in range(4)]
+        got = {}
+        for name, group in (("full", None), ("sharded", dist.new_group(backend="nccl"))):
+            pipe = serving.HostPipeline.for_engine(eng, nu + mi, d, users, k, _lgx.MODES["bf16x3"], upload_group=group)
+            outs = [torch.empty(nu, k, dtype=torch.int64).pin_memory() for _ in reqs]
+            for (hu, hi), out in zip(reqs, outs):
+                pipe.submit(hu, hi, out)
+            pipe.wait()
+            got[name] = [o.clone() for o in outs]
+        for a, b in zip(got["full"], got["sharded"]):
+            assert torch.equal(a, b)
+        assert not torch.equal(got["full"][0], got["full"][1])            # the requests really differ
     torch.cuda.synchronize()
     eng.close()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
