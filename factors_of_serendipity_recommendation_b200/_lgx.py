@@ -49,6 +49,7 @@ _SIGS = {
     "lgx_pack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "lgx_pack_operand": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lgx_score_topk_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lgx_score_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "lgx_score_topk": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                  _P, _P, _P, C.c_size_t, _P]),
     "lgx_topk_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
@@ -332,6 +333,13 @@ def pack_operand(src, row_ids, mode: int, is_items: bool):
     with torch.cuda.device(src.device):
         check(lib().lgx_pack_operand(ptr(src), ptr(row_ids), rows, d, mode, int(is_items), ptr(dst), stream()))
     return dst
+
+
+def score_plan(B: int, M: int, d: int, k: int, mode: int, sms: int = 0) -> dict:
+    """Host-only: the (user tile, item split) decomposition lgx_score_topk uses for this shape."""
+    out = (C.c_int32 * 4)()
+    check(lib().lgx_score_plan(B, M, d, k, mode, sms, out))
+    return {"user_tiles": out[0], "item_tiles": out[1], "splits": out[2], "tiles_per_split": out[3]}
 
 
 _topk_ws = {}

@@ -736,6 +736,26 @@ size_t lgx_score_topk_workspace_bytes(int32_t B, int32_t M, int32_t d, int32_t k
   return (size_t)plan.n_splits * B * k * 8 + (size_t)B * sizeof(unsigned) + 256;
 }
 
+int lgx_score_plan(int32_t B, int32_t M, int32_t d, int32_t k, int32_t mode, int32_t sms, int32_t* plan4) {
+  LGX_REQUIRE(plan4 != nullptr, "NULL argument");
+  LGX_REQUIRE(B > 0 && M > 0 && d > 0 && k > 0, "B, M, d, k must be positive");
+  LGX_REQUIRE(mode == LGX_SCORE_FP32 || mode == LGX_SCORE_BF16 || mode == LGX_SCORE_BF16X3, "unknown mode");
+  if (sms <= 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) sms = sm_count(); else { cudaGetLastError(); sms = 148; }
+  }
+  ScorePlan plan;
+  if (mode == LGX_SCORE_FP32) {
+    plan = plan_score(B, M, 64, 64, sms, 4);
+  } else {
+    TcConfig cfg = tc_config(d, k, mode);
+    if (!cfg.ok) cfg.tile_items = TcGeo<2>::TILE_I;
+    plan = tc_plan(B, M, cfg, sms);
+  }
+  plan4[0] = plan.n_user_tiles; plan4[1] = plan.n_item_tiles; plan4[2] = plan.n_splits; plan4[3] = plan.tiles_per_split;
+  return LGX_OK;
+}
+
 int lgx_score_topk(const lgx_graph* g, const void* U_op, const int64_t* users, int32_t B, const void* I_op, int32_t M,
                    int32_t d, int32_t k, int32_t mode, int64_t item_offset, int64_t* out_idx, float* out_val,
                    void* workspace, size_t workspace_bytes, lgx_stream stream) {

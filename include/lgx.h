@@ -169,8 +169,14 @@ int lgx_pack_operand(const float* src, const int64_t* row_ids, int32_t rows, int
  *                 Scores are RAW dot products (sigmoid is monotone; apply it to out_val if needed).
  *                 If fewer than k unmasked items exist the tail is filled with masked train items
  *                 carrying value -1024 like the reference (PT/Procedure.py:134).
+ * The workspace holds the per-split partial lists and, when a user tile's catalogue is split over several
+ * CTAs, one 32-bit bound per batch row through which those CTAs share the row's running threshold.
  */
 size_t lgx_score_topk_workspace_bytes(int32_t B, int32_t M, int32_t d, int32_t k, int32_t mode);
+/* Host-only: how lgx_score_topk decomposes a call on a device with `sms` SMs (0 = the current device, 148 when
+ * there is none).  plan4 = {user tiles, item tiles, splits per user tile, item tiles per split}.  The tcgen05
+ * modes pick the split count that minimises waves * (item tiles / splits + per-unit overhead); needs no GPU. */
+int lgx_score_plan(int32_t B, int32_t M, int32_t d, int32_t k, int32_t mode, int32_t sms, int32_t* plan4);
 int lgx_score_topk(const lgx_graph* g, const void* U_op, const int64_t* users, int32_t B,
                    const void* I_op, int32_t M, int32_t d, int32_t k, int32_t mode,
                    int64_t item_offset, int64_t* out_idx, float* out_val,

@@ -103,3 +103,33 @@ def test_synth_generator_contract():
     assert np.unique(u).size == 300 and np.unique(i).size == 500
     u2, i2 = synth.make_interactions(300, 500, 6000, seed=3)
     assert np.array_equal(u, u2) and np.array_equal(i, i2)
+
+
+def test_score_plan_is_wave_aware(lib):
+    """lgx_score_plan (host-only): the tcgen05 modes choose the number of catalogue splits per user tile so that
+    units / SMs is nearly integral, charging a per-unit overhead; the decomposition always covers the catalogue."""
+    from factors_of_serendipity_recommendation_b200 import _lgx
+    bf16 = _lgx.SCORE_BF16
+    # full Amazon-Book pass on 148 SMs: 412 user tiles = 2.78 waves; measured on B200: splitting loses -> 1 split
+    p = _lgx.score_plan(52643, 91599, 64, 20, bf16, sms=148)
+    assert (p["user_tiles"], p["item_tiles"], p["splits"]) == (412, 358, 1)
+    # 4096 users x 250 K items (BASELINE configs[4], one rank's shard): 32 user tiles; 9 splits = 288 units = 1.95 waves
+    p = _lgx.score_plan(4096, 250000, 64, 20, bf16, sms=148)
+    assert p["user_tiles"] == 32 and p["splits"] == 9
+    # one rank of 8 on Amazon-Book: 52 user tiles; 5 splits = 260 units = 1.76 waves (the old rule gave 156 = 1.05)
+    p = _lgx.score_plan(6581, 91599, 64, 20, bf16, sms=148)
+    assert p["user_tiles"] == 52 and p["splits"] == 5
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        B, M = int(rng.integers(1, 200000)), int(rng.integers(20, 3000000))
+        sms = int(rng.choice([1, 8, 132, 148, 160]))
+        mode = int(rng.choice([_lgx.SCORE_FP32, _lgx.SCORE_BF16, _lgx.SCORE_BF16X3]))
+        p = _lgx.score_plan(B, M, 64, 20, mode, sms=sms)
+        assert 1 <= p["splits"] <= 160                                  # kMaxSplits bounds the merge kernel's heads
+        assert p["splits"] * p["tiles_per_split"] >= p["item_tiles"]    # every item tile belongs to a split
+        assert (p["splits"] - 1) * p["tiles_per_split"] < p["item_tiles"]   # and no split is empty
+        p0 = _lgx.score_plan(B, M, 64, 20, mode)                        # sms = 0: the device the workspace is sized for
+        nbytes = lib.lgx_score_topk_workspace_bytes(B, M, 64, 20, mode)
+        assert nbytes >= p0["splits"] * B * 20 * 8 + (4 * B if p0["splits"] > 1 and mode != _lgx.SCORE_FP32 else 0)
+    with pytest.raises(RuntimeError):
+        _lgx.score_plan(0, 10, 64, 20, bf16)
