@@ -23,6 +23,9 @@ Parity is PINNED (not "parity unpinned") by:
   * tests/golden/mlls_train_step.npz      -- reference bpr_loss / backward / Adam step.
   * tests/golden/synth_small.npz          -- reference Loader + model on a synthetic graph
     with duplicate edges and isolated nodes.
+  * oracle/_ref/sampling*.so              -- the reference's OWN native BPR sampler, compiled from its single
+    source file where it lies under /root/reference (oracle/Makefile); ``sample_per_user`` and the device
+    sampler are checked against it (contract + distribution; its rand() stream cannot be matched).
 """
 from __future__ import annotations
 
@@ -276,6 +279,72 @@ def uniform_sample_python(n_users, m_items, train_size, all_pos, rng: np.random.
             break
         S.append([user, positem, negitem])
     return np.array(S)
+
+
+def sample_per_user(n_users, m_items, train_size, all_pos, rng: np.random.RandomState, neg_num: int = 1):
+    """Semantics of the reference's native sampler, sample_negative (PT/sources/sampling.cpp:27-56): EVERY user gets
+    exactly train_size // n_users rows [user, pos, neg...], pos uniform over the user's positives, each neg uniform
+    over the items that are not (rejection, :47-51).  The reference draws with rand() % n; the stream cannot be
+    matched, the distribution can (tests compare against the compiled reference in oracle/_ref when present)."""
+    per_user = train_size // n_users
+    S = np.empty((n_users * per_user, 2 + neg_num), dtype=np.int32)
+    row = 0
+    for user in range(n_users):
+        pos_for_user = all_pos[user]
+        for _ in range(per_user):
+            S[row, 0] = user
+            S[row, 1] = pos_for_user[rng.randint(0, len(pos_for_user))]
+            for j in range(neg_num):
+                while True:
+                    negitem = rng.randint(0, m_items)
+                    if negitem not in pos_for_user:
+                        break
+                S[row, 2 + j] = negitem
+            row += 1
+    return S
+
+
+def load_reference_sampler():
+    """The reference's own pybind11 sampler compiled by oracle/Makefile into oracle/_ref/ (built where
+    /root/reference exists; the .so travels to the GPU box).  None when it has not been built."""
+    import glob
+    import importlib.util
+    import os
+    hits = glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "sampling*.so"))
+    if not hits:
+        return None
+    spec = importlib.util.spec_from_file_location("sampling", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def check_bpr_triples(S: np.ndarray, all_pos, m_items: int, per_user: int | None = None) -> None:
+    """Contract every BPR sampler on this path honours (PT/utils.py:76-95, PT/sources/sampling.cpp:29-53):
+    pos is a train item of the user, neg is not, ids in range; per_user: the native sampler's exact user layout."""
+    S = np.asarray(S)
+    assert S.ndim == 2 and S.shape[1] >= 3
+    pos_sets = [set(int(x) for x in p) for p in all_pos]
+    assert S[:, 0].min() >= 0 and S[:, 0].max() < len(all_pos)
+    assert S[:, 1:].min() >= 0 and S[:, 1:].max() < m_items
+    for row in S:
+        ps = pos_sets[int(row[0])]
+        assert int(row[1]) in ps, "positive is not a train item of its user"
+        assert all(int(n) not in ps for n in row[2:]), "negative is a train item of its user"
+    if per_user is not None:
+        assert np.array_equal(S[:, 0], np.repeat(np.arange(len(all_pos)), per_user)), "per-user layout"
+
+
+def sampler_marginals(S: np.ndarray, all_pos, m_items: int, n_bins: int = 16):
+    """Two distribution summaries that do not depend on the RNG stream:
+    * histogram of the rank of pos inside its user's sorted positives, normalised to [0,1) -> uniform if pos ~ U(allPos[u]);
+    * histogram of neg over equal-width item-id bins (uniform over the user's non-positives, pooled over users)."""
+    S = np.asarray(S)
+    sorted_pos = [np.sort(np.asarray(p)) for p in all_pos]
+    frac = np.array([(np.searchsorted(sorted_pos[int(u)], int(p)) + 0.5) / len(sorted_pos[int(u)]) for u, p in S[:, :2]])
+    h_pos = np.histogram(frac, bins=n_bins, range=(0.0, 1.0))[0]
+    h_neg = np.histogram(S[:, 2], bins=n_bins, range=(0, m_items))[0]
+    return h_pos, h_neg
 
 
 # --------------------------------------------------------------------------- parity helpers

@@ -118,6 +118,47 @@ def test_device_sampler(mlls):
     assert P.shape == (ds.n_users * 3, 3) and np.array_equal(P[:, 0], np.repeat(np.arange(ds.n_users), 3))
 
 
+def test_device_sampler_vs_reference_native_sampler(mlls):
+    """lgx_sample_bpr(per_user=...) against the reference's OWN compiled sampler (oracle/_ref, PT/sources/sampling.cpp):
+    same contract, same layout, same pos / neg marginals (chi-square, 16 bins); and the Python-sampler mode against the
+    oracle's restatement of PT/utils.py:67-99."""
+    from factors_of_serendipity_recommendation_b200 import dataloader
+    from oracle import lightgcn_oracle as O
+    nu, mi = mlls["n_users"], mlls["m_items"]
+    ds = dataloader.InteractionDataset(nu, mi, mlls["train_user"], mlls["train_item"], device="cuda")
+    all_pos = [[] for _ in range(nu)]
+    for u, i in zip(mlls["train_user"].tolist(), mlls["train_item"].tolist()):
+        all_pos[u].append(i)
+
+    def chi2(a, b):
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        ka, kb = np.sqrt(b.sum() / a.sum()), np.sqrt(a.sum() / b.sum())
+        keep = (a + b) > 0
+        return float((((ka * a - kb * b) ** 2) / (a + b))[keep].sum())
+
+    S_dev = ds.getGraphHandle().sample_bpr(0, per_user=40, seed=11).cpu().numpy()
+    O.check_bpr_triples(S_dev, all_pos, mi, per_user=40)
+    ref = O.load_reference_sampler()
+    if ref is not None:
+        ref.seed(2020)
+        S_ref = np.asarray(ref.sample_negative(nu, mi, 40 * nu, all_pos, 1))
+    else:                                                   # the restatement (itself checked against oracle/_ref on CPU)
+        S_ref = O.sample_per_user(nu, mi, 40 * nu, all_pos, np.random.RandomState(3))
+    assert S_dev.shape == S_ref.shape
+    for h_dev, h_ref in zip(O.sampler_marginals(S_dev, all_pos, mi), O.sampler_marginals(S_ref, all_pos, mi)):
+        assert chi2(h_dev, h_ref) < 37.7                    # dof 15, p = 0.999
+    # Python-sampler semantics (users drawn with replacement)
+    n = 40 * nu
+    S_dev = ds.getGraphHandle().sample_bpr(n, per_user=0, seed=5).cpu().numpy()
+    O.check_bpr_triples(S_dev, all_pos, mi)
+    S_py = O.uniform_sample_python(nu, mi, n, all_pos, np.random.RandomState(1))
+    for h_dev, h_ref in zip(O.sampler_marginals(S_dev, all_pos, mi), O.sampler_marginals(S_py, all_pos, mi)):
+        assert chi2(h_dev, h_ref) < 37.7
+    hu_dev = np.histogram(S_dev[:, 0], bins=16, range=(0, nu))[0]
+    hu_py = np.histogram(S_py[:, 0], bins=16, range=(0, nu))[0]
+    assert chi2(hu_dev, hu_py) < 37.7
+
+
 def test_train_epoch_runs_and_learns(mlls, train_step):
     from factors_of_serendipity_recommendation_b200 import Procedure, utils, world
     t = train_step

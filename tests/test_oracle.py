@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import scipy.sparse as sp
 import torch
 
@@ -106,3 +107,56 @@ def test_topk_validity_checker():
     assert O.topk_is_valid(r, np.array([1, 3]), 2)          # tie at rank 2
     assert not O.topk_is_valid(r, np.array([1, 4]), 2)
     assert not O.topk_is_valid(r, np.array([2, 3]), 2)      # misses the strict top-1
+
+
+def _all_pos(mlls):
+    pos = [[] for _ in range(mlls["n_users"])]
+    for u, i in zip(mlls["train_user"].tolist(), mlls["train_item"].tolist()):
+        pos[u].append(i)
+    return pos
+
+
+def _chi2_two_sample(a, b):
+    """Chi-square statistic for 'two histograms come from one distribution' (dof = bins - 1)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    ka, kb = np.sqrt(b.sum() / a.sum()), np.sqrt(a.sum() / b.sum())
+    keep = (a + b) > 0
+    return float((((ka * a - kb * b) ** 2) / (a + b))[keep].sum())
+
+
+def test_native_sampler_restatement_vs_compiled_reference(mlls):
+    """oracle.sample_per_user restates PT/sources/sampling.cpp:27-56; the reference's own sampler compiled into
+    oracle/_ref (oracle/Makefile) honours the same contract and has the same pos / neg marginals."""
+    ref = O.load_reference_sampler()
+    if ref is None:
+        pytest.skip("oracle/_ref sampler not built (needs /root/reference; __graft_entry__.build() makes it)")
+    all_pos = _all_pos(mlls)
+    nu, mi = mlls["n_users"], mlls["m_items"]
+    train_num = 40 * nu + 17                                   # 40 triples per user; the remainder is dropped (:29)
+    ref.seed(2020)
+    S_ref = np.asarray(ref.sample_negative(nu, mi, train_num, all_pos, 1))
+    assert S_ref.dtype == np.int32 and S_ref.shape == (40 * nu, 3)
+    O.check_bpr_triples(S_ref, all_pos, mi, per_user=40)
+    S_own = O.sample_per_user(nu, mi, train_num, all_pos, np.random.RandomState(7))
+    assert S_own.shape == S_ref.shape and S_own.dtype == S_ref.dtype
+    O.check_bpr_triples(S_own, all_pos, mi, per_user=40)
+    hp_r, hn_r = O.sampler_marginals(S_ref, all_pos, mi)
+    hp_o, hn_o = O.sampler_marginals(S_own, all_pos, mi)
+    # 16 bins -> dof 15: chi2 < 37.7 holds with p = 0.999 when the distributions agree
+    assert _chi2_two_sample(hp_r, hp_o) < 37.7
+    assert _chi2_two_sample(hn_r, hn_o) < 37.7
+
+
+def test_bpr_triple_checker_rejects_bad_samples(mlls):
+    all_pos = _all_pos(mlls)
+    mi = mlls["m_items"]
+    good = O.sample_per_user(mlls["n_users"], mi, 2 * mlls["n_users"], all_pos, np.random.RandomState(0))
+    O.check_bpr_triples(good, all_pos, mi, per_user=2)
+    bad = good.copy()
+    bad[5, 2] = bad[5, 1]                                      # a train item as the negative
+    with pytest.raises(AssertionError):
+        O.check_bpr_triples(bad, all_pos, mi)
+    bad = good.copy()
+    bad[3, 0] = (bad[3, 0] + 1) % mlls["n_users"]              # breaks the per-user layout (and most likely the positive)
+    with pytest.raises(AssertionError):
+        O.check_bpr_triples(bad, all_pos, mi, per_user=2)
