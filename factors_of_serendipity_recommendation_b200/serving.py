@@ -16,6 +16,23 @@ import torch
 from . import _lgx
 
 
+def upload_slices(rank: int, world: int, n_rows: int, n_users: int):
+    """Rows of the stacked [users; items] table that ``rank`` uploads: chunk = ceil(n_rows / world) rows from
+    rank * chunk.  -> (chunk, user_part, item_part) where each part is (dst_lo, dst_hi, src_lo, src_hi) — rows
+    [dst_lo, dst_hi) of the rank's local chunk come from rows [src_lo, src_hi) of the host user / item table — or
+    None when the rank's range does not touch that table.  Pure index arithmetic (tests/test_parallel_cpu.py)."""
+    chunk = (n_rows + world - 1) // world
+    r0 = rank * chunk
+    r1 = min(n_rows, r0 + chunk)
+    user_part = item_part = None
+    if r0 < min(r1, n_users):
+        user_part = (0, min(r1, n_users) - r0, r0, min(r1, n_users))
+    if max(r0, n_users) < r1:
+        lo = max(r0, n_users)
+        item_part = (lo - r0, r1 - r0, lo - n_users, r1 - n_users)
+    return chunk, user_part, item_part
+
+
 class HostPipeline:
     """Double-buffered full-catalogue top-K over host-resident embedding tables.
 
@@ -112,13 +129,11 @@ class HostPipeline:
                 tables[nu:].copy_(host_item, non_blocking=True)
             else:
                 import torch.distributed as dist
-                r0 = self.rank * self.chunk                      # my rows [r0, r1) of the stacked [users; items] table
-                r1 = min(self.n_rows, r0 + self.chunk)
-                local = self.local[b]
-                if r0 < min(r1, nu):
-                    local[:min(r1, nu) - r0].copy_(host_user[r0:min(r1, nu)], non_blocking=True)
-                if max(r0, nu) < r1:
-                    local[max(r0, nu) - r0:r1 - r0].copy_(host_item[max(r0, nu) - nu:r1 - nu], non_blocking=True)
+                local = self.local[b]                            # my 1/world of the stacked [users; items] rows
+                _, user_part, item_part = upload_slices(self.rank, self.world, self.n_rows, nu)
+                for part, host in ((user_part, host_user), (item_part, host_item)):
+                    if part is not None:
+                        local[part[0]:part[1]].copy_(host[part[2]:part[3]], non_blocking=True)
                 dist.all_gather_into_tensor(self.padded[b], local, group=self.group)
             self.uploaded[b].record(self.s_up)
         with torch.cuda.stream(self.s_comp):

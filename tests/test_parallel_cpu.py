@@ -102,3 +102,35 @@ def test_partition_and_merge_single_process():
     cv = torch.tensor([[[2.0, 1.0]], [[2.0, 0.5]]])
     idx, val = parallel.merge_candidates_reference(ci, cv, 3)
     assert idx.tolist() == [[5, 7, 1]] and val.tolist() == [[2.0, 2.0, 1.0]]
+
+
+def test_upload_slices_tile_the_stacked_table():
+    """serving.upload_slices (sharded host upload at N > 1): over all ranks the slices reproduce the stacked
+    [users; items] table exactly once, in the padded all-gather layout rank * chunk + local row."""
+    from factors_of_serendipity_recommendation_b200.serving import upload_slices
+    rng = np.random.default_rng(0)
+    cases = [(52643, 91599, 8), (10, 3, 4), (3, 10, 4), (1, 1, 2), (5, 0, 3), (7, 9, 1), (100, 100, 7)]
+    cases += [(int(rng.integers(1, 500)), int(rng.integers(0, 500)), int(rng.integers(1, 17))) for _ in range(200)]
+    for nu, mi, world in cases:
+        n_rows = nu + mi
+        users = np.arange(nu) + 1_000_000
+        items = np.arange(mi) + 2_000_000
+        stacked = np.concatenate([users, items])
+        chunk = None
+        gathered = None
+        for rank in range(world):
+            c, up, ip = upload_slices(rank, world, n_rows, nu)
+            if chunk is None:
+                chunk = c
+                gathered = np.full(chunk * world, -1, dtype=np.int64)
+            assert c == chunk and chunk * world >= n_rows
+            local = np.full(chunk, -1, dtype=np.int64)
+            for part, host in ((up, users), (ip, items)):
+                if part is not None:
+                    d0, d1, s0, s1 = part
+                    assert 0 <= d0 < d1 <= chunk and 0 <= s0 < s1 <= len(host) and d1 - d0 == s1 - s0
+                    assert np.all(local[d0:d1] == -1)                   # user and item parts do not overlap
+                    local[d0:d1] = host[s0:s1]
+            gathered[rank * chunk:(rank + 1) * chunk] = local
+        assert np.array_equal(gathered[:n_rows], stacked)
+        assert np.all(gathered[n_rows:] == -1)                          # only padding is left unwritten
