@@ -11,9 +11,15 @@
 //               accumulators double-buffered in TMEM (2 x 256 columns), tcgen05.commit -> mbarriers
 //   warp 2      TMEM allocator / deallocator
 //   warps 4-11  epilogue: each thread owns one user row (TMEM lane) and one 128-column half of the
-//               tile: tcgen05.ld 32 columns at a time, max-filter against the row's running K-th
-//               score, rare slow path = train-mask binary search + sorted insert into the thread's
-//               private top-K list (shared memory, column layout).
+//               tile: tcgen05.ld 32 columns at a time (double-buffered in registers), train items of
+//               the row overwritten with -inf by a monotone cursor over the user's sorted CSR row,
+//               3-input-max filter over 4 groups of 8 columns against the row's bound, survivors
+//               appended to a shared-memory queue, queues flushed warp-convergently into a
+//               register-resident sorted top-K list.  The bound is the best of: the thread's own
+//               K-th score, the partner half's published bound, max_j min(a_j, b_{K-j}) over both
+//               halves' quartile ranks, and (when the catalogue is split over CTAs) the row's bound
+//               shared through global memory.  Operand rows past the end are NaN-filled by TMA, so
+//               out-of-range columns and users need no code.
 // bf16x3 mode runs the same kernel with K = 3d over split operands (hi.hi + hi.lo + lo.hi).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -225,7 +231,6 @@ struct EpiState {
   float tu;                     // what I last published to thr_mine
   bool use_union;
   unsigned* gbound;             // this row's slot of TcParams::row_bound, or NULL
-  __device__ __forceinline__ float thresh() const { return lv[KMAX - 1]; }
   // Filter threshold: a score must beat my own K-th best, and must be >= the partner's K-th best -- the
   // partner already holds K items of this row at least that good, so anything below it cannot reach the
   // row's final top-K (equal scores are kept: the final merge breaks ties by item id).
