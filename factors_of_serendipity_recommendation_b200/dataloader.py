@@ -55,7 +55,47 @@ def parse_interactions(path: str):
     """'uid item item ...' per line (PT/dataloader.py:247-262) -> (unique users, users[E], items[E]).
 
     Lines with a user id and no items are skipped (the reference crashes on them; the TF loader
-    skips them, TF/utility/load_data.py:42-45 -- amazon-book/test.txt has 4 such lines)."""
+    skips them, TF/utility/load_data.py:42-45 -- amazon-book/test.txt has 4 such lines).
+
+    The reference parses line by line in Python (one list comprehension + two ``extend`` per user).  Here the whole
+    file is converted in one C pass (np.fromstring, whitespace-separated integers) and the line structure comes from
+    the byte array: token starts by vectorised compares, tokens per line by a binary search of the newline offsets,
+    the user column by np.repeat.  Same output (tests/test_abi.py), about 2x faster on an Amazon-Book-sized train.txt."""
+    import warnings
+    raw = np.fromfile(path, dtype=np.uint8)
+    empty = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    if raw.size == 0:
+        return empty
+    is_nl = raw == 10
+    is_space = is_nl | (raw == 32) | (raw == 13) | (raw == 9)
+    starts = np.flatnonzero(is_space[:-1] & ~is_space[1:]) + 1       # first byte of every token
+    if not is_space[0]:
+        starts = np.concatenate(([0], starts))
+    if starts.size == 0:
+        return empty
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                               # numpy only WARNS when it stops at a bad token
+        try:
+            values = np.fromstring(raw.tobytes(), dtype=np.int64, sep=" ")
+        except (DeprecationWarning, ValueError) as e:
+            raise ValueError(f"{path}: not a whitespace-separated integer file ({e})") from None
+    if values.size != starts.size:
+        raise ValueError(f"{path}: {starts.size} tokens but {values.size} integers parsed")
+    # tokens per line: tokens that start before each newline (and the unterminated last line)
+    line_ends = np.concatenate((np.flatnonzero(is_nl), [raw.size]))
+    upto = np.searchsorted(starts, line_ends, side="left")
+    per_line = np.diff(np.concatenate(([0], upto)))
+    first_tok_of_line = upto - per_line
+    keep_line = per_line >= 2                                         # a user id and at least one item
+    uniq = values[first_tok_of_line[keep_line]]
+    drop = np.zeros(values.size, dtype=bool)                          # user-id tokens and id-only lines
+    drop[first_tok_of_line[per_line >= 1]] = True
+    items = values[~drop]
+    return uniq, np.repeat(uniq, per_line[keep_line] - 1), items
+
+
+def parse_interactions_lines(path: str):
+    """The reference's line loop (PT/dataloader.py:247-262), kept as the checker for parse_interactions."""
     uniq, us, its = [], [], []
     with open(path) as f:
         for line in f:

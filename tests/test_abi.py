@@ -66,6 +66,25 @@ def test_parse_interactions(tmp_path):
     assert us.tolist() == [0, 0, 0, 1, 5, 5] and its.tolist() == [3, 4, 5, 2, 1, 1]
     u, i = dataloader.parse_interactions(os.path.join(GOLD, "mlls_train.txt"))[1:]
     assert u.size == 63687 and u.max() == 607 and i.max() == 2119
+    # the one-pass tokenizer returns exactly what the reference's line loop (PT/dataloader.py:247-262) returns
+    for name in ("mlls_train.txt", "mlls_test.txt"):
+        a = dataloader.parse_interactions(os.path.join(GOLD, name))
+        b = dataloader.parse_interactions_lines(os.path.join(GOLD, name))
+        assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, b))
+    cases = {"empty": "", "blank": "\n\n", "idonly": "5\n7 1 2\n9\n", "noeol": "1 2 3\n4 5",
+             "spaces": "  1  2   3 \n\n 4 6\r\n", "one": "3 4", "big": "123456789012 7 99999999999\n"}
+    for name, text in cases.items():
+        q = tmp_path / name
+        q.write_text(text)
+        toks = [line.split() for line in text.split("\n")]
+        got = dataloader.parse_interactions(str(q))
+        assert got[0].tolist() == [int(t[0]) for t in toks if len(t) >= 2], name
+        assert got[1].tolist() == [int(t[0]) for t in toks if len(t) >= 2 for _ in t[1:]], name
+        assert got[2].tolist() == [int(v) for t in toks if len(t) >= 2 for v in t[1:]], name
+    bad = tmp_path / "bad"
+    bad.write_text("1 2 x 3\n")
+    with pytest.raises(ValueError):
+        dataloader.parse_interactions(str(bad))
 
 
 def test_metrics_match_oracle():
