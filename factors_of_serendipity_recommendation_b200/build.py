@@ -15,7 +15,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "liblgx.so")
-SOURCES = ["lgx_graph.cu", "lgx_spmm.cu", "lgx_score.cu", "lgx_score_tc.cu", "lgx_train.cu"]
+SOURCES = ["lgx_graph.cu", "lgx_spmm.cu", "lgx_score.cu", "lgx_score_tc.cu", "lgx_score_gq.cu", "lgx_train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

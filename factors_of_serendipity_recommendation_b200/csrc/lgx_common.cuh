@@ -11,7 +11,9 @@ namespace lgx {
 
 void set_error(const std::string& msg);
 int device_ok();   // LGX_OK iff current device is sm_100; sets the error otherwise
-int sm_count();
+int sm_count();          // of the current device
+int current_device();
+constexpr int kMaxDevices = 64;
 
 #define LGX_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \

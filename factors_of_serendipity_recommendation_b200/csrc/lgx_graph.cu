@@ -37,15 +37,24 @@ int device_ok() {
   return LGX_OK;
 }
 
+// Per device: a process may drive several GPUs (one per stream / thread), so nothing here is cached process-wide.
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return dev;
+}
+
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  int v = cached[dev];             // racing threads compute the same value
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    cached[dev] = v;
   }
-  return cached;
+  return v;
 }
 
 // ------------------------------------------------------------------------------------ kernels

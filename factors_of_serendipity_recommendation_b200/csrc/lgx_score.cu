@@ -265,10 +265,11 @@ int score_topk_fp32(const lgx_graph* g, const float* U, const int64_t* users, in
   float* ws_val = reinterpret_cast<float*>(workspace);
   int32_t* ws_idx = reinterpret_cast<int32_t*>(ws_val + (size_t)plan.n_splits * B * K);
   const size_t smem = fp32_smem_bytes(K);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[kMaxDevices] = {};     // the opt-in is a per-device function attribute
+  const int dev = current_device();
+  if (dev >= kMaxDevices || smem > configured[dev]) {
     LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    if (dev < kMaxDevices) configured[dev] = smem;
   }
   const TrainMask mask = make_mask(g);
   dim3 grid(plan.n_user_tiles, plan.n_splits);

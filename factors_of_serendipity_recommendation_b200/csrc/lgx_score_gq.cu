@@ -1,0 +1,1160 @@
+// Fused full-catalogue scoring + train mask + top-K on the 5th-gen tensor cores (sm_100a), "group queue" kernel.
+//
+// Replaces getUsersRating (PT/model.py:179-184), the train-item mask (PT/Procedure.py:129-134) and torch.topk
+// (:135).  The [B, M] score matrix lives only in TMEM.
+//
+// What changed against the first tcgen05 kernel (lgx_score_tc.cu, kept for A/B runs): that kernel's epilogue spent
+// 5 issue slots per score, ~85 % of them outside the max filter: per-column candidate appends (a warp holds 32
+// independent rows, so "rare per row" is "always" per warp), the train-mask sweep and the mask cursor's dependent
+// global loads.  Here
+//   * the TRAIN MASK IS APPLIED BY THE TENSOR CORE: two helper warps walk the 128 rows' sorted train lists and, per
+//     item tile, give every row that has train items in the tile one K-slot of a small mask operand pair in shared
+//     memory: A_mask[row, slot] = -2^100, B_mask[col, slot] = 1 for the row's train columns.  One or two extra
+//     K = 16 MMA steps add -2^100 to exactly the train (row, col) scores, so the epilogue has no mask code at all;
+//   * the epilogue keeps the top-K GROUPS of 8 columns by group maximum (the 3-input max tree it needs anyway):
+//     a candidate is one predicated (max, group id) append per group instead of an 8-column scan.  The K-th best
+//     group maximum is a valid lower bound on the row's K-th best score (K distinct items score at least that),
+//     so every item of the final top-K lies in one of the K kept groups;
+//   * a second small kernel (k_rescore_topk, one warp per row) recomputes the 8K scores of the kept groups from the
+//     same bf16 operands in fp32, re-applies the mask exactly and emits the sorted top-K (ties by item id).
+//
+//   warp 0      TMA producer (user tile resident, item K-blocks [256 x 64] bf16 through an mbarrier ring)
+//   warp 1      MMA issuer: tcgen05.mma.kind::f16 M128 N256 K16 into double-buffered fp32 TMEM accumulators,
+//               the tile's mask steps, then the real K steps
+//   warp 2      TMEM alloc / dealloc
+//   warp 3      mask builder: scatters the tile's pre-bucketed train entries (k_mask_buckets) into a ring of two
+//               32-slot mask buffers
+//   warps 4-11  epilogue: one thread = one user row x one 128-column half of the tile
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "lgx_common.cuh"
+#include "lgx_score_plan.cuh"
+#include "lgx_topk.cuh"
+#include "lgx_tc_ptx.cuh"
+
+namespace lgx {
+
+TrainMask make_mask(const lgx_graph* g);
+int make_operand_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int box_rows);
+
+constexpr int GQ_TILE_U = 128;                  // UMMA M: one TMEM lane per user
+constexpr int GQ_TILE_I = 256;                  // UMMA N
+constexpr int GQ_KBLK = 64;                     // bf16 per K block = one 128-byte swizzle row
+constexpr int GQ_A_BLOCK = GQ_TILE_U * GQ_KBLK * 2;   // 16 KB
+constexpr int GQ_STAGE = GQ_TILE_I * GQ_KBLK * 2;     // 32 KB
+constexpr int GQ_EPI = 256;                     // epilogue threads
+constexpr int GQ_THREADS = 128 + GQ_EPI;
+constexpr int GQ_MAX_STAGES = 6;
+constexpr int GQ_TMEM_BUF = 256;
+constexpr int GQ_GROUP = 8;                     // columns per candidate group
+constexpr int GQ_SMEM_LIMIT = 232448;
+constexpr uint32_t GQ_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GQ_TILE_I >> 3) << 17) |
+                              ((uint32_t)(GQ_TILE_U >> 4) << 24);
+constexpr unsigned short GQ_BF16_ONE = 0x3F80;       // 1.0
+constexpr unsigned short GQ_BF16_NEG_BIG = 0xF180;   // -2^100: finite (0 * it stays 0), below any real score
+
+struct GqParams {
+  int B, M, K;
+  int k_blocks, stages;
+  int q_cap;
+  int union_bound;
+  int n_splits, tiles_per_split;
+  int has_mask;
+  int dbg;                // LGX_GQ_DEBUG (experiments): 1 = TMEM loads only, 2 = no TMEM loads either, 4 = no mask,
+                          // 8 = masks built but no mask MMA issued, 32 = no pre-bucketing (in-kernel list walk)
+  int64_t item_offset;
+  TrainMask mask;
+  const int64_t* users;
+  float* ws_val;          // [n_splits, B, K] group maxima, best first
+  int32_t* ws_idx;        // [n_splits, B, K] group ids (local item id / 8)
+  unsigned* row_bound;    // [B] or NULL (n_splits == 1)
+  // pre-bucketed train entries (k_mask_buckets); mk_region == NULL: every user tile walks its lists in the kernel
+  const int64_t* mk_region;
+  const int32_t* mk_ptr;
+  const uint16_t* mk_entries;
+};
+
+__device__ __forceinline__ unsigned gq_ord_encode(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float gq_ord_decode(unsigned u) {
+  return u == 0u ? -CUDART_INF_F : __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// byte offset of element (row, k) in a K-major [rows x 64] bf16 tile with the 128-byte swizzle
+__device__ __forceinline__ uint32_t gq_swz(int row, int k) {
+  return (uint32_t)row * 128u + (uint32_t)((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1));
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------ mask buckets
+// The in-kernel mask builder must publish one mask per ~700 cycles.  Walking 128 sorted train lists tile by tile
+// (cursor, dirty ballots, slot ranks, undo records) took ~460 instructions per tile -- ncu showed the builder warps
+// 94 % busy and the epilogue starved -- so that irregular part runs ahead of time, massively parallel, in a small
+// pre-kernel: one CTA per user tile buckets the tile's train entries by item tile (count, scan, fill) into
+//     ptr[u_tile][n_tiles + 1], entries[region[u_tile] + ptr ..] = (row << 8 | column), 16 bits each, any order.
+// The builder then only scatters ~20 pre-bucketed entries per tile.  The entry area is a bump allocator sized for
+// the usual case; a user tile that does not fit gets region = -1 and the main kernel walks its lists itself.
+struct GqBucketParams {
+  TrainMask mask;
+  const int64_t* users;
+  int B, M, n_tiles;
+  int64_t item_offset;
+  unsigned long long* cursor;     // bump allocator state (zeroed by the caller)
+  unsigned long long cap;         // entries available
+  int64_t* region;                // [n_user_tiles]
+  int32_t* ptr;                   // [n_user_tiles][n_tiles + 1]
+  uint16_t* entries;
+};
+
+constexpr int MB_THREADS = 1024;      // latency-bound (one dependent global load per entry): many threads per user tile
+__global__ void __launch_bounds__(MB_THREADS)
+k_mask_buckets(const GqBucketParams bp) {
+  extern __shared__ int s_cnt[];                 // [n_tiles + 1]
+  __shared__ int64_t s_lo[GQ_TILE_U];            // first in-range CSR entry of every row
+  __shared__ int s_pre[GQ_TILE_U + 1];           // exclusive prefix of the rows' in-range lengths
+  __shared__ int s_warp[MB_THREADS / 32];
+  __shared__ long long s_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ut = blockIdx.x;
+  const int n1 = bp.n_tiles + 1;
+  const int32_t bias = (int32_t)(bp.mask.n_users + bp.item_offset);
+  const bool whole = bp.mask.m_items_hint > 0 && bp.item_offset == 0 && bp.M >= bp.mask.m_items_hint;   // the whole catalogue: no searches
+  for (int i = tid; i < n1; i += MB_THREADS) s_cnt[i] = 0;
+  if (tid < GQ_TILE_U) {
+    const int u = ut * GQ_TILE_U + tid;
+    int64_t lo = 0, hi = 0;
+    if (u < bp.B) {
+      const int64_t uid = bp.users ? bp.users[u] : (int64_t)u;
+      const int64_t r0 = bp.mask.indptr[uid], r1 = bp.mask.indptr[uid + 1];
+      lo = r0; hi = r1;
+      if (!whole) {
+        int64_t a = r0, b = r1;                     // first entry >= bias
+        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(bp.mask.indices + m) < bias) a = m + 1; else b = m; }
+        lo = a;
+        b = r1;                                     // first entry >= bias + M
+        const int64_t key = (int64_t)bias + bp.M;
+        while (a < b) { const int64_t m = (a + b) >> 1; if ((int64_t)__ldg(bp.mask.indices + m) < key) a = m + 1; else b = m; }
+        hi = a;
+      }
+    }
+    s_lo[tid] = lo;
+    // inclusive scan of the lengths over the 128 rows (4 warps)
+    int incl = (int)(hi - lo);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    s_pre[tid + 1] = incl;                          // warp-local for now
+  }
+  __syncthreads();
+  if (tid < GQ_TILE_U) {
+    int add = 0;
+    for (int w2 = 0; w2 < warp; ++w2) add += s_warp[w2];
+    s_pre[tid + 1] += add;
+  }
+  if (tid == 0) s_pre[0] = 0;
+  __syncthreads();
+  const int total = s_pre[GQ_TILE_U];
+  // the tile's entries as one flat range: thread-strided, every load independent of the others
+  auto locate = [&](int idx, int& row) -> int64_t {
+    int a = 0, b = GQ_TILE_U;                       // last row with s_pre[row] <= idx
+    while (b - a > 1) { const int m = (a + b) >> 1; if (s_pre[m] <= idx) a = m; else b = m; }
+    row = a;
+    return s_lo[a] + (idx - s_pre[a]);
+  };
+  for (int idx = tid; idx < total; idx += MB_THREADS) {
+    int row;
+    const int64_t e = locate(idx, row);
+    atomicAdd(&s_cnt[(__ldg(bp.mask.indices + e) - bias) >> 8], 1);
+  }
+  __syncthreads();
+  // exclusive scan of s_cnt[0 .. n_tiles): thread t owns a contiguous chunk
+  const int chunk = (n1 + MB_THREADS - 1) / MB_THREADS;
+  const int c0 = min(tid * chunk, n1), c1 = min(c0 + chunk, n1);
+  int sum = 0;
+  for (int i = c0; i < c1; ++i) sum += s_cnt[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();                                  // s_warp is reused
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int base = incl - sum;
+  for (int w2 = 0; w2 < warp; ++w2) base += s_warp[w2];
+  for (int i = c0; i < c1; ++i) { const int v = s_cnt[i]; s_cnt[i] = base; base += v; }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long tot = (unsigned long long)s_cnt[bp.n_tiles];
+    const unsigned long long at = atomicAdd(bp.cursor, tot);
+    s_base = (at + tot <= bp.cap) ? (long long)at : -1;
+    bp.region[ut] = s_base;
+  }
+  __syncthreads();
+  if (s_base < 0) return;
+  for (int i = tid; i < n1; i += MB_THREADS) bp.ptr[(int64_t)ut * n1 + i] = s_cnt[i];
+  __syncthreads();
+  uint16_t* out = bp.entries + s_base;
+  for (int idx = tid; idx < total; idx += MB_THREADS) {
+    int row;
+    const int64_t e = locate(idx, row);
+    const int c = __ldg(bp.mask.indices + e) - bias;
+    out[atomicAdd(&s_cnt[c >> 8], 1)] = (uint16_t)((row << 8) | (c & 255));
+  }
+}
+
+// Fallback cursor (a user tile whose entries did not fit the bucket area): one dependent load per train item.
+struct GqCursor {
+  const int32_t* idx;
+  int64_t cur, end;
+  int32_t bias, next;
+  __device__ __forceinline__ void init(const TrainMask& m, int64_t uid, int64_t item_offset, int first_local) {
+    idx = m.indices; cur = end = 0; next = INT32_MAX; bias = 0;
+    if (m.indptr == nullptr || uid < 0) return;
+    bias = (int32_t)(m.n_users + item_offset);
+    int64_t lo = m.indptr[uid], hi = m.indptr[uid + 1];
+    end = hi;
+    const int32_t key = bias + first_local;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(idx + mid) < key) lo = mid + 1; else hi = mid; }
+    cur = lo;
+    next = cur < end ? __ldg(idx + cur) - bias : INT32_MAX;
+  }
+  __device__ __forceinline__ void advance() {
+    ++cur;
+    next = cur < end ? __ldg(idx + cur) - bias : INT32_MAX;
+  }
+};
+
+// Per-thread epilogue state: the top-K groups of this thread's half of the row, sorted best-first in registers
+// (right-aligned in KMAX slots), a shared-memory candidate queue that only the warp-convergent flush drains, and
+// the row-threshold exchange with the thread that owns the other half (see lgx_score_tc.cu for the derivation).
+template <int KMAX, bool SHARE>
+struct GqEpi {
+  float lv[KMAX];
+  int32_t li[KMAX];
+  float* qhead; float* qbase;
+  float* thr_mine; const float* thr_other;
+  float4* quart_mine; const float4* quart_other;
+  float tu;
+  bool use_union;
+  unsigned* gbound;
+  static constexpr int ROW = GQ_EPI * 2;
+  __device__ __forceinline__ float filter() const {
+    return max3(lv[KMAX - 1], tu, *reinterpret_cast<const volatile float*>(thr_other));
+  }
+  __device__ __forceinline__ void init(int K) {
+#pragma unroll
+    for (int p = 0; p < KMAX; ++p) {
+      lv[p] = p < KMAX - K ? CUDART_INF_F : -CUDART_INF_F;
+      li[p] = INT32_MAX;
+    }
+    tu = -CUDART_INF_F;
+  }
+  __device__ __forceinline__ void append(float s, int32_t j) {
+    qhead[0] = s;
+    reinterpret_cast<int32_t*>(qhead)[GQ_EPI] = j;
+    qhead += ROW;
+  }
+  __device__ __forceinline__ bool fuller_than(int rows) const { return qhead > qbase + rows * ROW; }
+  // groups reach a thread in ascending id order, so an equal maximum loses the tie: strict '>'
+  __device__ __forceinline__ void insert(float x, int32_t xi) {
+#pragma unroll
+    for (int p = KMAX - 1; p >= 1; --p) {
+      const bool gp = x > lv[p], gq = x > lv[p - 1];
+      lv[p] = gp ? (gq ? lv[p - 1] : x) : lv[p];
+      li[p] = gp ? (gq ? li[p - 1] : xi) : li[p];
+    }
+    const bool g0 = x > lv[0];
+    lv[0] = g0 ? x : lv[0];
+    li[0] = g0 ? xi : li[0];
+  }
+  __device__ __forceinline__ void flush() {
+    const unsigned gb = (SHARE && gbound) ? *reinterpret_cast<const volatile unsigned*>(gbound) : 0u;
+    for (const float* a = qbase; a < qhead; a += ROW) insert(a[0], reinterpret_cast<const int32_t*>(a)[GQ_EPI]);
+    qhead = qbase;
+    float t = lv[KMAX - 1];
+    if (use_union) {
+      const float a1 = lv[KMAX / 4 - 1], a2 = lv[KMAX / 2 - 1], a3 = lv[3 * KMAX / 4 - 1];
+      const volatile float4* o = quart_other;
+      const float b1 = o->x, b2 = o->y, b3 = o->z, b4 = o->w;
+      *quart_mine = make_float4(a1, a2, a3, t);
+      t = fmaxf(max3(fminf(a1, b3), fminf(a2, b2), fminf(a3, b1)), fmaxf(t, b4));
+    }
+    if (SHARE && gbound) {
+      const unsigned mine = (t != t) ? 0u : gq_ord_encode(t);
+      if (mine > gb) atomicMax(gbound, mine);
+      t = fmaxf(t, gq_ord_decode(gb));
+    }
+    const int tb = __float_as_int(t);                  // publish prev_float(bound); -inf stays -inf
+    tu = (t == -CUDART_INF_F || t != t) ? -CUDART_INF_F
+                                       : __int_as_float(tb > 0 ? tb - 1 : (tb == 0 ? (int)0x80000001 : tb + 1));
+    *thr_mine = tu;
+    __syncwarp();
+  }
+};
+
+// 32 columns = 4 groups: 3-input max tree per group, one predicated append per group.  NaN scores (operand rows
+// past the end, filled by TMA) are ignored by max and fail '>'.
+template <int KMAX, bool SHARE>
+__device__ __forceinline__ void gq_chunk(const uint32_t (&v)[32], int gid0, GqEpi<KMAX, SHARE>& st, float th) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float a = max3(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+    const float b = max3(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+    const float m = max3(a, b, fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+    if (m > th) st.append(m, gid0 + g);
+  }
+}
+
+template <int KMAX, bool SMALLQ, bool SHARE>
+__global__ void __launch_bounds__(GQ_THREADS, 1)
+k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_i,
+                const GqParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = smem_dyn + (base - raw);
+  const uint32_t sA = base;
+  const uint32_t off_am = (uint32_t)p.k_blocks * GQ_A_BLOCK;          // A_mask [128 x 64] bf16
+  const uint32_t off_bm = off_am + GQ_A_BLOCK;                         // B_mask [256 x 64] bf16
+  const uint32_t off_stages = off_bm + GQ_STAGE;
+  const uint32_t off_queue = off_stages + (uint32_t)p.stages * GQ_STAGE;
+  const uint32_t sAm = base + off_am, sBm = base + off_bm, sB = base + off_stages;
+  // final lists are staged over the idle B ring (KMAX * 256 * 8 <= 64 KB <= 2 stages)
+  float* lval_all = reinterpret_cast<float*>(gbase + off_stages);
+  int32_t* lidx_all = reinterpret_cast<int32_t*>(gbase + off_stages + (size_t)KMAX * GQ_EPI * 4);
+  const uint32_t off_bar = off_queue + (uint32_t)p.q_cap * GQ_EPI * 8;
+  const uint32_t bar_full = base + off_bar;                       // [stages]
+  const uint32_t bar_empty = bar_full + 8 * GQ_MAX_STAGES;        // [stages]
+  const uint32_t bar_a = bar_empty + 8 * GQ_MAX_STAGES;
+  const uint32_t bar_tfull = bar_a + 8;                           // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
+  // mask buffers: the 64-slot mask operand is a ring of two 32-slot buffers (K steps {0,1} and {2,3})
+  const uint32_t bar_mfull = bar_tempty + 16;                     // [b] the builder published buffer b
+  const uint32_t bar_mfree = bar_mfull + 16;                      // [b] the MMAs that read buffer b retired
+  constexpr uint32_t kBarBytes = 8 * (2 * GQ_MAX_STAGES + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + off_bar + kBarBytes);
+  volatile int* mcnt = reinterpret_cast<volatile int*>(gbase + off_bar + kBarBytes + 8);    // [b] slots used | more << 8
+  constexpr uint32_t kMiscBytes = 24;                                                      // tmem slot + mcnt
+  float* thr_all = reinterpret_cast<float*>(gbase + off_bar + kBarBytes + kMiscBytes);     // [EPI]
+  float4* quart_all = reinterpret_cast<float4*>(gbase + off_bar + kBarBytes + kMiscBytes + 4 * GQ_EPI);   // [EPI], 16-byte aligned
+
+  // Roles: warps 0-7 epilogue, warp 8 TMA, warp 9 MMA, warp 10 TMEM alloc, warp 11 mask builder.  The single-lane
+  // helper roles get the HIGHEST warp ids: the issue arbiter prefers higher warp ids, and the helpers (one per SM
+  // sub-partition, each sharing it with two epilogue warps) are the serial resources of the pipeline.
+  const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = hw_warp < 8 ? hw_warp + 4 : hw_warp - 8;      // role index: 0 TMA, 1 MMA, 2 alloc, 3 builder, 4-11 epilogue
+  const int u_tile = blockIdx.x, split = blockIdx.y;
+  const int n_tiles = (p.M + GQ_TILE_I - 1) / GQ_TILE_I;
+  const int t_begin = split * p.tiles_per_split;
+  const int n_my = max(0, min(n_tiles, t_begin + p.tiles_per_split) - t_begin);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_u)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_i)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, GQ_EPI);
+      mbar_init(bar_mfull + 8 * b, 1);
+      mbar_init(bar_mfree + 8 * b, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < GQ_EPI) {
+    thr_all[threadIdx.x] = -CUDART_INF_F;
+    if (p.union_bound) quart_all[threadIdx.x] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+  }
+  if (p.has_mask) {
+    // mask operands start as zeros: (GQ_A_BLOCK + GQ_STAGE) / 16 = 3072 16-byte stores over 384 threads
+    for (uint32_t o = threadIdx.x * 16u; o < (uint32_t)(GQ_A_BLOCK + GQ_STAGE); o += GQ_THREADS * 16u)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sAm + o), "r"(0u) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (n_my > 0) {
+      // ---------------------------------------------------------------- TMA producer (converged warp, one lane issues)
+      if (elect_one()) {
+        mbar_expect_tx(bar_a, (uint32_t)p.k_blocks * GQ_A_BLOCK);
+        for (int kb = 0; kb < p.k_blocks; ++kb)
+          tma_load_2d(sA + kb * GQ_A_BLOCK, &tmap_u, bar_a, kb * GQ_KBLK, u_tile * GQ_TILE_U);
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int row0 = (t_begin + it) * GQ_TILE_I;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait<false>(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_full + 8 * stage, GQ_STAGE);
+            tma_load_2d(sB + stage * GQ_STAGE, &tmap_i, bar_full + 8 * stage, kb * GQ_KBLK, row0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (n_my > 0) {
+      // ---------------------------------------------------------------- MMA issuer (converged warp, one lane issues)
+      // This warp is the serial resource of the pipeline: everything it needs per tile is kept in registers and
+      // advanced incrementally (barrier addresses, the B descriptor, phases), the three barriers a tile needs are
+      // polled by three lanes in ONE try_wait, and the tile loop body exists twice so the TMEM buffer is static.
+      mbar_wait<false>(bar_a, 0);
+      tc_fence_after();
+      const uint64_t adesc_m = umma_desc_sw128(sAm), bdesc_m = umma_desc_sw128(sBm);
+      const uint64_t adesc0 = umma_desc_sw128(sA);
+      const uint64_t bdesc0 = umma_desc_sw128(sB);
+      int stage = 0;
+      uint32_t phase = 0;               // parity of the B ring
+      uint32_t mrc = 0u;                // mask rounds consumed: buffer = mrc & 1
+      auto tile = [&](int it, const int buf) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * GQ_TMEM_BUF;
+        const uint32_t tpar = (uint32_t)((it >> 1) & 1) ^ 1u;
+        uint32_t acc = 0u;
+        if (p.has_mask) {
+          // The tile's train mask first: one K = 16 step per 16 published slots puts -2^100 into the (row, train
+          // column) accumulators; the real K steps then accumulate on top.  Mask first, so a buffer is released as
+          // soon as its own MMAs retire instead of behind the tile's real MMAs.
+          uint32_t b = mrc & 1u;
+          mbar_wait3(bar_tempty + 8 * buf, tpar, bar_mfull + 8 * b, (mrc >> 1) & 1u, bar_full + 8 * stage, phase, lane);
+          tc_fence_after();
+          for (;;) {
+            ++mrc;
+            const int v = mcnt[b];
+            const int n = v & 255;
+            if (elect_one()) {
+              if (n > 0) tc_mma_f16(tmem_d, adesc_m + (uint64_t)(4 * b), bdesc_m + (uint64_t)(4 * b), GQ_IDESC, acc);
+              if (n > 16) tc_mma_f16(tmem_d, adesc_m + (uint64_t)(4 * b + 2), bdesc_m + (uint64_t)(4 * b + 2), GQ_IDESC, 1u);
+              tc_commit(bar_mfree + 8 * b);
+            }
+            __syncwarp();
+            if (n > 0) acc = 1u;
+            if (!(v >> 8)) break;
+            b = mrc & 1u;                 // a tile with more than 32 dirty rows: further rounds
+            mbar_wait<false>(bar_mfull + 8 * b, (mrc >> 1) & 1u);
+            tc_fence_after();
+          }
+        } else {
+          mbar_wait3(bar_tempty + 8 * buf, tpar, bar_full + 8 * stage, phase, bar_full + 8 * stage, phase, lane);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (kb > 0) {
+            mbar_wait<false>(bar_full + 8 * stage, phase);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint64_t adesc = adesc0 + (uint64_t)(kb * (GQ_A_BLOCK >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (GQ_STAGE >> 4));
+            tc_mma_f16(tmem_d, adesc, bdesc, GQ_IDESC, acc);
+            tc_mma_f16(tmem_d, adesc + 2, bdesc + 2, GQ_IDESC, 1u);
+            tc_mma_f16(tmem_d, adesc + 4, bdesc + 4, GQ_IDESC, 1u);
+            tc_mma_f16(tmem_d, adesc + 6, bdesc + 6, GQ_IDESC, 1u);
+            tc_commit(bar_empty + 8 * stage);
+            if (kb == p.k_blocks - 1) tc_commit(bar_tfull + 8 * buf);   // accumulator tile complete
+          }
+          __syncwarp();
+          acc = 1u;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      };
+      for (int it = 0; it < n_my; it += 2) {
+        tile(it, 0);
+        if (it + 1 < n_my) tile(it + 1, 1);
+      }
+    }
+  } else if (warp < 4) {
+    // -------------------------------------------------------------------- mask builder (warp 3)
+    if (warp == 3 && p.has_mask && n_my > 0) {
+      const unsigned lt = (1u << lane) - 1u;
+      uint32_t rc = 0;                    // rounds published: buffer = rc & 1
+      // what this lane wrote into buffer b the last time (shared-memory addresses, 0 = nothing), or the whole
+      // buffer was written by a multi-pass round and is cleared wholesale
+      uint32_t uA0 = 0, uB0 = 0, uA1 = 0, uB1 = 0;
+      bool wide0 = false, wide1 = false;
+      // zero what the previous use of buffer b wrote; then every lane may write again
+      auto reclaim = [&](uint32_t b) {
+        mbar_wait<false>(bar_mfree + 8 * b, ((rc >> 1) & 1u) ^ 1u);     // the MMAs that read this buffer have retired
+        ++rc;
+        const bool wide = b ? wide1 : wide0;
+        if (wide) {
+          // both K steps of the buffer, all 384 operand rows: 2 x 2 16-byte chunks per row
+          for (int i = lane; i < (GQ_TILE_U + GQ_TILE_I) * 4; i += 32) {
+            const int rrow = i >> 2, ch = (int)(4 * b) + (i & 3);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};"
+                         ::"r"(sAm + (uint32_t)rrow * 128u + (uint32_t)((ch ^ (rrow & 7)) << 4)), "r"(0u) : "memory");
+          }
+        } else {
+          const uint32_t a = b ? uA1 : uA0, c = b ? uB1 : uB0;
+          if (c) { st_shared_u16(a, 0); st_shared_u16(c, 0); }
+        }
+        if (b) { uA1 = uB1 = 0; wide1 = false; } else { uA0 = uB0 = 0; wide0 = false; }
+        __syncwarp();     // a slot changes owner between rounds: all zeroing before any new write
+      };
+      auto publish = [&](uint32_t b, int n, bool more) {
+        if (lane == 0) mcnt[b] = ((p.dbg & 8) ? 0 : n) | (more ? 256 : 0);
+        if (!(p.dbg & 64))                 // experiment 64: no proxy fence (timing only, results are wrong)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_mfull + 8 * b);
+      };
+      const int64_t region = p.mk_region ? p.mk_region[u_tile] : -1;
+      if (p.dbg & 16) {                   // experiment 16: handshake only, nothing is built
+        for (int it = 0; it < n_my; ++it) {
+          const uint32_t b = rc & 1u;
+          reclaim(b);
+          publish(b, 0, false);
+        }
+      } else if (region >= 0) {
+        // ---- fast path: the tile's entries are pre-bucketed; entries and offsets are fetched two tiles ahead
+        const int32_t* ptrw = p.mk_ptr + (int64_t)u_tile * (n_tiles + 1);
+        const uint16_t* ents = p.mk_entries + region;
+        int wbase = -(1 << 30), pw = 0;
+        auto getptr = [&](int t) {        // warp-uniform; a 32-tile window of offsets lives in one register per lane
+          if (t - wbase >= 32 || t < wbase) { wbase = t; pw = __ldg(ptrw + min(t + lane, n_tiles)); }
+          return __shfl_sync(0xffffffffu, pw, t - wbase);
+        };
+        // Three prefetch slots used round-robin by a 3x unrolled tile loop: a slot's entry load is issued two tiles before
+        // its use and never moved between registers (a rotating copy made every iteration wait for its own load).
+        struct Pre { int e0, n; uint32_t ent; };
+        Pre s0{0, 0, 0u}, s1{0, 0, 0u}, s2{0, 0, 0u};
+        auto fetch = [&](Pre& q, int it2) {
+          q.e0 = 0; q.n = 0; q.ent = 0u;
+          if (it2 < n_my) {
+            const int t = t_begin + it2;
+            q.e0 = getptr(t);
+            q.n = getptr(t + 1) - q.e0;
+            if (lane < q.n) q.ent = __ldg(ents + q.e0 + lane);
+          }
+        };
+        auto process = [&](const Pre& q) {
+          const int n_e = q.n, e0 = q.e0;
+          const uint32_t ent = q.ent;
+          if (n_e <= 32) {
+            const bool valid = lane < n_e;
+            const int row = (int)(ent >> 8), col = (int)(ent & 255u);
+            const unsigned bit = valid ? 1u << (row & 31) : 0u;
+            const int ws = row >> 5;
+            const unsigned m0 = __reduce_or_sync(0xffffffffu, ws == 0 ? bit : 0u);
+            const unsigned m1 = __reduce_or_sync(0xffffffffu, ws == 1 ? bit : 0u);
+            const unsigned m2 = __reduce_or_sync(0xffffffffu, ws == 2 ? bit : 0u);
+            const unsigned m3 = __reduce_or_sync(0xffffffffu, ws == 3 ? bit : 0u);
+            const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), n_dirty = c2 + __popc(m3);
+            const unsigned mw = ws == 0 ? m0 : (ws == 1 ? m1 : (ws == 2 ? m2 : m3));
+            const int rank = (ws == 0 ? 0 : (ws == 1 ? c0 : (ws == 2 ? c1 : c2))) + __popc(mw & ((1u << (row & 31)) - 1u));
+            const int nrounds = n_dirty > 32 ? (n_dirty + 31) >> 5 : 1;
+            for (int r = 0; r < nrounds; ++r) {
+              const uint32_t b = rc & 1u;
+              reclaim(b);
+              if (valid && (rank >> 5) == r) {
+                const int slot = 32 * (int)b + (rank & 31);
+                const uint32_t a = sAm + gq_swz(row, slot), c = sBm + gq_swz(col, slot);
+                st_shared_u16(a, GQ_BF16_NEG_BIG);      // several entries of one row write the same value
+                st_shared_u16(c, GQ_BF16_ONE);
+                if (b) { uA1 = a; uB1 = c; } else { uA0 = a; uB0 = c; }
+              }
+              publish(b, min(32, n_dirty - 32 * r), r + 1 < nrounds);
+            }
+          } else {
+            // more than 32 train entries in one 128 x 256 tile: pass 1 collects the dirty rows, every round
+            // re-reads the entries it needs; the buffer is cleared wholesale afterwards
+            unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            for (int cbase = 0; cbase < n_e; cbase += 32) {
+              const bool valid = cbase + lane < n_e;
+              const uint32_t e = valid ? (uint32_t)__ldg(ents + e0 + cbase + lane) : 0u;
+              const int row = (int)(e >> 8), ws = row >> 5;
+              const unsigned bit = valid ? 1u << (row & 31) : 0u;
+              m0 |= __reduce_or_sync(0xffffffffu, ws == 0 ? bit : 0u);
+              m1 |= __reduce_or_sync(0xffffffffu, ws == 1 ? bit : 0u);
+              m2 |= __reduce_or_sync(0xffffffffu, ws == 2 ? bit : 0u);
+              m3 |= __reduce_or_sync(0xffffffffu, ws == 3 ? bit : 0u);
+            }
+            const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), n_dirty = c2 + __popc(m3);
+            const int nrounds = n_dirty > 32 ? (n_dirty + 31) >> 5 : 1;
+            for (int r = 0; r < nrounds; ++r) {
+              const uint32_t b = rc & 1u;
+              reclaim(b);
+              for (int cbase = 0; cbase < n_e; cbase += 32) {
+                if (cbase + lane < n_e) {
+                  const uint32_t e = (uint32_t)__ldg(ents + e0 + cbase + lane);
+                  const int row = (int)(e >> 8), col = (int)(e & 255u), ws = row >> 5;
+                  const unsigned mw = ws == 0 ? m0 : (ws == 1 ? m1 : (ws == 2 ? m2 : m3));
+                  const int rank = (ws == 0 ? 0 : (ws == 1 ? c0 : (ws == 2 ? c1 : c2))) + __popc(mw & ((1u << (row & 31)) - 1u));
+                  if ((rank >> 5) == r) {
+                    const int slot = 32 * (int)b + (rank & 31);
+                    st_shared_u16(sAm + gq_swz(row, slot), GQ_BF16_NEG_BIG);
+                    st_shared_u16(sBm + gq_swz(col, slot), GQ_BF16_ONE);
+                  }
+                }
+              }
+              if (b) wide1 = true; else wide0 = true;
+              publish(b, min(32, n_dirty - 32 * r), r + 1 < nrounds);
+            }
+          }
+        };
+        fetch(s0, 0);
+        fetch(s1, 1);
+        for (int it = 0; it < n_my; it += 3) {
+          fetch(s2, it + 2);
+          process(s0);
+          if (it + 1 < n_my) { fetch(s0, it + 3); process(s1); }
+          if (it + 2 < n_my) { fetch(s1, it + 4); process(s2); }
+        }
+      } else {
+        // ---- fallback: walk the 128 sorted train lists here (4 rows per lane, one dependent load per train item)
+        GqCursor cur[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const int u = u_tile * GQ_TILE_U + x * 32 + lane;
+          const int64_t uid = (u < p.B) ? (p.users ? p.users[u] : (int64_t)u) : -1;
+          cur[x].init(p.mask, uid, p.item_offset, t_begin * GQ_TILE_I);
+        }
+        for (int it = 0; it < n_my; ++it) {
+          const int tile_lo = (t_begin + it) * GQ_TILE_I, tile_hi = tile_lo + GQ_TILE_I;
+          int rank[4], n = 0;
+          bool dirty[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            dirty[x] = cur[x].next < tile_hi;
+            const unsigned bal = __ballot_sync(0xffffffffu, dirty[x]);
+            rank[x] = n + __popc(bal & lt);
+            n += __popc(bal);
+          }
+          const int nrounds = n > 32 ? (n + 31) >> 5 : 1;
+          for (int r = 0; r < nrounds; ++r) {
+            const uint32_t b = rc & 1u;
+            reclaim(b);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              if (dirty[x] && (rank[x] >> 5) == r) {
+                const int slot = 32 * (int)b + (rank[x] & 31);
+                st_shared_u16(sAm + gq_swz(x * 32 + lane, slot), GQ_BF16_NEG_BIG);
+                while (cur[x].next < tile_hi) {
+                  st_shared_u16(sBm + gq_swz(cur[x].next - tile_lo, slot), GQ_BF16_ONE);
+                  cur[x].advance();
+                }
+              }
+            }
+            if (b) wide1 = true; else wide0 = true;
+            publish(b, min(32, n - 32 * r), r + 1 < nrounds);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (256 threads)
+    const int q = hw_warp & 3;                // TMEM lane quarter this warp may access (hardware warp id % 4)
+    const int h = hw_warp >> 2;               // which 128-column half of the tile
+    const int row = q * 32 + lane;
+    const int col = h * GQ_TILE_U + row;
+    GqEpi<KMAX, SHARE> st;
+    st.init(p.K);
+    st.qbase = st.qhead = reinterpret_cast<float*>(gbase + off_queue) + col;
+    st.thr_mine = thr_all + col;
+    st.thr_other = thr_all + (h ^ 1) * GQ_TILE_U + row;
+    st.quart_mine = quart_all + col;
+    st.quart_other = quart_all + (h ^ 1) * GQ_TILE_U + row;
+    st.use_union = p.K == KMAX && p.union_bound;
+    st.gbound = (SHARE && u_tile * GQ_TILE_U + row < p.B) ? p.row_bound + (u_tile * GQ_TILE_U + row) : nullptr;
+    if (SHARE) st.flush();
+    const int u = u_tile * GQ_TILE_U + row;
+    for (int it = 0; it < n_my; ++it) {
+      const int buf = it & 1;
+      mbar_wait<false>(bar_tfull + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GQ_TMEM_BUF + h * 128);
+      const int gid_base = ((t_begin + it) * GQ_TILE_I + h * 128) / GQ_GROUP;
+      if (p.dbg & 2) {                        // experiment: barrier handshake only (TMA / MMA / builder floor)
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * buf);
+        continue;
+      }
+      const float th = (p.dbg & 1) ? CUDART_INF_F : st.filter();   // experiment 1: loads + max tree, nothing appended
+      // Three register buffers: the loads of the first three chunks are issued back to back and the fourth as soon as
+      // the first chunk is consumed, so the TMEM buffer goes back to the MMA warp after ONE chunk of epilogue work
+      // instead of three.  The accumulator round trip (epilogue hold time + MMA latency) over two TMEM buffers is what
+      // bounds this kernel: a tile is only 512 tensor cycles of work (K = d = 64).  LGX_KEEP pins a buffer's values
+      // across the issue of later loads (otherwise the compiler folds the buffers into one set of registers).
+      uint32_t va[32], vb[32], vc[32];
+      LGX_TMEM_LD32(va, taddr);
+      LGX_TMEM_LD32(vb, taddr + 32);
+      LGX_TMEM_LD32(vc, taddr + 64);
+      LGX_TMEM_WAIT(va);
+      LGX_KEEP(vb);
+      LGX_KEEP(vc);
+      gq_chunk<KMAX, SHARE>(va, gid_base, st, th);
+      LGX_TMEM_LD32(va, taddr + 96);
+      LGX_TMEM_WAIT(va);
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);      // the whole tile half is in registers: the TMEM buffer may be overwritten
+      LGX_KEEP(vb);
+      LGX_KEEP(vc);
+      gq_chunk<KMAX, SHARE>(vb, gid_base + 4, st, th);
+      if (SMALLQ) { __syncwarp(); if (__any_sync(0xffffffffu, st.fuller_than(p.q_cap - 8))) st.flush(); }
+      gq_chunk<KMAX, SHARE>(vc, gid_base + 8, st, th);
+      gq_chunk<KMAX, SHARE>(va, gid_base + 12, st, th);
+      __syncwarp();
+      if (__any_sync(0xffffffffu, st.fuller_than(p.q_cap - (SMALLQ ? 8 : 16)))) st.flush();
+    }
+    st.flush();
+    // stage the register lists, merge the two halves of every row and publish the split's K best groups
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      lval_all[k * GQ_EPI + col] = st.lv[k];
+      lidx_all[k * GQ_EPI + col] = st.li[k];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GQ_EPI) : "memory");
+    if (h == 0 && u < p.B) {
+      int pa = KMAX - p.K, pb = KMAX - p.K;
+      const int64_t o = ((int64_t)split * p.B + u) * p.K;
+      for (int k = 0; k < p.K; ++k) {
+        const float av = lval_all[pa * GQ_EPI + row], bv = lval_all[pb * GQ_EPI + GQ_TILE_U + row];
+        const int32_t ai = lidx_all[pa * GQ_EPI + row], bi = lidx_all[pb * GQ_EPI + GQ_TILE_U + row];
+        const bool take_b = better(bv, bi, av, ai);
+        p.ws_val[o + k] = take_b ? bv : av;
+        p.ws_idx[o + k] = take_b ? bi : ai;
+        pa += take_b ? 0 : 1;
+        pb += take_b ? 1 : 0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ rescoring
+// One warp per batch row.  The row's candidate lists hold (group maximum, group id); T = the largest K-th entry
+// over the row's lists is a lower bound on the row's K-th best score, so only groups with maximum >= T can hold
+// a top-K item (for a single list: all K of them).  Their 8 items each are scored again from the same bf16 operands
+// with fp32 accumulation -- as a [16 items x k] x [k x 8] mma.sync per pair of groups, the user vector replicated
+// over the 8 columns: an fp32 FMA loop with bf16 unpacking measured 330 us for the Amazon-Book pass, 75 % of it
+// integer unpack instructions.  Train items are dropped by binary search in the row's sorted train list, items
+// within `margin` of T are collected and ranked by counting.
+struct GqRescoreParams {
+  const float* ws_val; const int32_t* ws_idx;
+  int P, B, K, M, ktot;
+  const __nv_bfloat16* U_op; const __nv_bfloat16* I_op;
+  TrainMask mask; const int64_t* users;
+  int64_t item_offset;
+  int64_t* out_idx; float* out_val;
+};
+
+constexpr int RS_WARPS = 8;
+constexpr int RS_CAP = 160;      // candidate buffer per warp: compressed to the best K whenever > RS_CAP - 64 are held
+constexpr int RS_KMAX = 32;
+constexpr int RS_KTOT_MAX = 384;
+constexpr int RS_GLIST = 64;     // selected groups staged per warp
+
+// rank-by-counting compression of buf[0..n) to its best min(n, K) entries, sorted best-first (score desc, id asc)
+__device__ __forceinline__ int rs_compress(float* bv, int32_t* bi, float* tv, int32_t* ti, int n, int K, int lane) {
+  for (int e = lane; e < n; e += 32) {
+    const float v = bv[e];
+    const int32_t i = bi[e];
+    int rank = 0;
+    for (int f = 0; f < n; ++f) rank += better(bv[f], bi[f], v, i) ? 1 : 0;
+    if (rank < K) { tv[rank] = v; ti[rank] = i; }
+  }
+  __syncwarp();
+  const int m = min(n, K);
+  for (int e = lane; e < m; e += 32) { bv[e] = tv[e]; bi[e] = ti[e]; }
+  __syncwarp();
+  return m;
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct RsRow {
+  float* bv; int32_t* bi; float* tv; int32_t* ti;
+  int n;
+};
+
+// Collect the items that can still reach the top-K.  Train items are NOT filtered here: a binary search is six dependent global loads, and doing one per tile
+// (10 per row) was most of the first version's 250 us; rs_drop_masked checks all collected items in one pass.
+__device__ __forceinline__ void rs_push(const GqRescoreParams& rp, float sc, int64_t j, bool ok, float T_lo, RsRow& row,
+                                        int lane) {
+  const bool keep = ok && j < rp.M && sc >= T_lo;
+  const unsigned kbits = __ballot_sync(0xffffffffu, keep);
+  if (keep) {
+    const int pos = row.n + __popc(kbits & ((1u << lane) - 1u));
+    row.bv[pos] = sc;
+    row.bi[pos] = (int32_t)j;
+  }
+  row.n += __popc(kbits);
+}
+
+// remove the row's train items from the buffer (one binary search per buffered item, all in parallel)
+__device__ __forceinline__ void rs_drop_masked(const GqRescoreParams& rp, int64_t uid, RsRow& row, int lane) {
+  if (rp.mask.indptr == nullptr) return;
+  int kept = 0;
+  for (int e0 = 0; e0 < row.n; e0 += 32) {
+    const int e = e0 + lane;
+    float v = 0.f;
+    int32_t i = 0;
+    bool keep = false;
+    if (e < row.n) {
+      v = row.bv[e];
+      i = row.bi[e];
+      keep = !rp.mask.contains(uid, rp.item_offset + i);
+    }
+    const unsigned kb = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) {
+      const int pos = kept + __popc(kb & ((1u << lane) - 1u));     // pos <= e: in-place compaction is safe per 32-batch
+      row.bv[pos] = v;
+      row.bi[pos] = i;
+    }
+    kept += __popc(kb);
+    __syncwarp();
+  }
+  row.n = kept;
+}
+
+// mma.sync m16n8k16 with the ITEMS as the B operand (n = 8 items of one group, so one 16-byte load per lane is
+// exactly two steps' {b0, b1} -- no register shuffling) and the user vector replicated over the 16 rows of A.
+// Lane (g = lane / 4, t = lane % 4) loads the 8 consecutive k [32 kb + 8t, +8) of item g; they feed logical k
+// {2t, 2t+1, 2t+8, 2t+9} of two k16 steps, and the user fragment uses the same permutation, so the dot product is
+// unchanged.  D[row][2t], D[row][2t+1] = scores of items 2t, 2t+1 of the group in every lane of every quad.
+__device__ __forceinline__ void rs_process(const GqRescoreParams& rp, const int32_t* glist, int cnt, const uint4* us,
+                                           int64_t uid, float T_lo, RsRow& row, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int kb32 = rp.ktot >> 5;            // even: ktot is a multiple of 64
+  for (int m = 0; m < cnt; m += 4) {        // four groups per pass
+    const uint4* pr[4];
+    int32_t gid[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      gid[q] = glist[m + q < cnt ? m + q : m];
+      // rows past the end of the catalogue are clamped for the load and dropped in rs_push
+      const int64_t j = min((int64_t)gid[q] * GQ_GROUP + g, (int64_t)rp.M - 1);
+      pr[q] = reinterpret_cast<const uint4*>(rp.I_op + j * rp.ktot) + t;
+    }
+    float c[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
+    for (int kb = 0; kb < kb32; kb += 2) {
+      uint4 x[2][4];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[jj][q] = __ldg(pr[q] + 4 * (kb + jj));
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const uint4 xu = us[4 * (kb + jj) + t];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          mma_bf16_16816(c[q], xu.x, xu.x, xu.y, xu.y, x[jj][q].x, x[jj][q].y);
+          mma_bf16_16816(c[q], xu.z, xu.z, xu.w, xu.w, x[jj][q].z, x[jj][q].w);
+        }
+      }
+    }
+    // quad g < 4 publishes group g: its lane t holds items 2t and 2t+1
+    const float sa = g == 0 ? c[0][0] : (g == 1 ? c[1][0] : (g == 2 ? c[2][0] : c[3][0]));
+    const float sb = g == 0 ? c[0][1] : (g == 1 ? c[1][1] : (g == 2 ? c[2][1] : c[3][1]));
+    const int32_t gg = g == 0 ? gid[0] : (g == 1 ? gid[1] : (g == 2 ? gid[2] : gid[3]));
+    const bool ok = g < 4 && m + g < cnt;
+    const int64_t j0 = (int64_t)gg * GQ_GROUP + 2 * t;
+    rs_push(rp, sa, j0, ok, T_lo, row, lane);
+    rs_push(rp, sb, j0 + 1, ok, T_lo, row, lane);
+    __syncwarp();
+    if (row.n > RS_CAP - 64) {
+      rs_drop_masked(rp, uid, row, lane);
+      row.n = rs_compress(row.bv, row.bi, row.tv, row.ti, row.n, rp.K, lane);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_rescore_topk(const GqRescoreParams rp) {
+  __shared__ __align__(16) __nv_bfloat16 s_user[RS_WARPS][RS_KTOT_MAX];
+  __shared__ float s_bv[RS_WARPS][RS_CAP];
+  __shared__ int32_t s_bi[RS_WARPS][RS_CAP];
+  __shared__ float s_tv[RS_WARPS][RS_KMAX];
+  __shared__ int32_t s_ti[RS_WARPS][RS_KMAX];
+  __shared__ int32_t s_gl[RS_WARPS][RS_GLIST];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * RS_WARPS + wib;
+  if (u >= rp.B) return;
+  const int K = rp.K, P = rp.P, ktot = rp.ktot;
+  RsRow row{s_bv[wib], s_bi[wib], s_tv[wib], s_ti[wib], 0};
+  {
+    const uint4* ur = reinterpret_cast<const uint4*>(rp.U_op + (int64_t)u * ktot);
+    uint4* dst = reinterpret_cast<uint4*>(s_user[wib]);
+    for (int c = lane; c < ktot / 8; c += 32) dst[c] = __ldg(ur + c);
+  }
+  // T = max over lists of their K-th entry; vtop = the row's best group maximum
+  float T = -CUDART_INF_F, vtop = -CUDART_INF_F;
+  for (int pp = lane; pp < P; pp += 32) {
+    const int64_t o = ((int64_t)pp * rp.B + u) * K;
+    T = fmaxf(T, rp.ws_val[o + K - 1]);
+    vtop = fmaxf(vtop, rp.ws_val[o]);
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, s));
+    vtop = fmaxf(vtop, __shfl_xor_sync(0xffffffffu, vtop, s));
+  }
+  // tensor-core and mma.sync fp32 sums of the same products differ by O(ktot * 2^-24) relative to sum |products|
+  const float margin = (T == -CUDART_INF_F) ? 0.f : 1e-4f * fmaxf(fabsf(T), fabsf(vtop)) + 1e-30f;
+  const float T_lo = T - margin;
+  const int64_t uid = rp.users ? rp.users[u] : (int64_t)u;
+  __syncwarp();
+  const uint4* us = reinterpret_cast<const uint4*>(s_user[wib]);
+  int32_t* glist = s_gl[wib];
+  int cnt = 0;
+  const int total = P * K;
+  for (int e0 = 0; e0 < total; e0 += 32) {
+    const int e = e0 + lane;
+    float gv = -CUDART_INF_F;
+    int32_t gid = INT32_MAX;
+    if (e < total) {
+      const int pp = e / K, k = e - pp * K;
+      const int64_t o = ((int64_t)pp * rp.B + u) * K + k;
+      gv = rp.ws_val[o];
+      gid = rp.ws_idx[o];
+    }
+    const bool sel = gid != INT32_MAX && gv >= T;
+    const unsigned sb = __ballot_sync(0xffffffffu, sel);
+    if (sel) glist[cnt + __popc(sb & ((1u << lane) - 1u))] = gid;
+    cnt += __popc(sb);
+    __syncwarp();
+    if (cnt > RS_GLIST - 32) {
+      rs_process(rp, glist, cnt, us, uid, T_lo, row, lane);
+      cnt = 0;
+      __syncwarp();
+    }
+  }
+  rs_process(rp, glist, cnt, us, uid, T_lo, row, lane);
+  rs_drop_masked(rp, uid, row, lane);
+  const int n = rs_compress(row.bv, row.bi, row.tv, row.ti, row.n, K, lane);
+  for (int k = lane; k < n; k += 32) {
+    rp.out_val[(int64_t)u * K + k] = row.bv[k];
+    rp.out_idx[(int64_t)u * K + k] = (int64_t)row.bi[k] + rp.item_offset;
+  }
+  if (n < K && lane == 0) {
+    // fewer than K unmasked items: the reference's index_put_(-1024) + topk returns train items next
+    // (PT/Procedure.py:134-135); a shard with fewer than K items pads with (-inf, -1), merged away later
+    int got = n;
+    if (rp.mask.indptr != nullptr) {
+      for (int64_t qq = rp.mask.indptr[uid]; qq < rp.mask.indptr[uid + 1] && got < K; ++qq) {
+        const int64_t it = (int64_t)rp.mask.indices[qq] - rp.mask.n_users;
+        if (it >= rp.item_offset && it < rp.item_offset + rp.M) {
+          rp.out_val[(int64_t)u * K + got] = kMaskValue;
+          rp.out_idx[(int64_t)u * K + got] = it;
+          ++got;
+        }
+      }
+    }
+    for (; got < K; ++got) {
+      rp.out_val[(int64_t)u * K + got] = -CUDART_INF_F;
+      rp.out_idx[(int64_t)u * K + got] = -1;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------- host
+struct GqConfig { int k_blocks, stages, q_cap, union_bound; size_t smem; bool ok; };   // also declared in lgx_score_tc.cu
+
+GqConfig gq_config(int d, int K, int mode) {
+  GqConfig c{};
+  const int ktot = mode == LGX_SCORE_BF16X3 ? 3 * d : d;
+  c.ok = (d % GQ_KBLK == 0) && K >= 1 && K <= 32 && ktot <= RS_KTOT_MAX;
+  c.k_blocks = ktot / GQ_KBLK;
+  static const int forced_q = [] { const char* e = std::getenv("LGX_SCORE_QCAP"); return e ? std::atoi(e) : 0; }();
+  static const int union_env = [] { const char* e = std::getenv("LGX_SCORE_UNION"); return e ? std::atoi(e) : 1; }();
+  // queue depth vs B-ring depth, first fit: 32-row queues with >= 3 ring stages, else 24 / 16 / 8 rows with >= 2
+  const int cands[4] = {32, 24, 16, 8};
+  bool found = false;
+  for (int i = 0; i < 4 && !found; ++i) {
+    const int qc = cands[i];
+    if (forced_q && qc != forced_q) continue;
+    size_t fx = 1024 + (size_t)c.k_blocks * GQ_A_BLOCK + GQ_A_BLOCK + GQ_STAGE + (size_t)qc * GQ_EPI * 8 +
+                8 * (2 * GQ_MAX_STAGES + 9) + 24 + (size_t)(4 + 16) * GQ_EPI + 16;
+    const int need = (qc == 32 && !forced_q) ? 3 : 2;
+    int uni = union_env ? 1 : 0;
+    if (uni && qc == 8 && fx + (size_t)need * GQ_STAGE > GQ_SMEM_LIMIT) {    // last resort: drop the 4 KB quartile array
+      uni = 0;
+      fx -= (size_t)16 * GQ_EPI;
+    }
+    if (fx + (size_t)need * GQ_STAGE > GQ_SMEM_LIMIT) continue;
+    c.q_cap = qc;
+    c.union_bound = uni;
+    c.stages = (int)std::min<size_t>(GQ_MAX_STAGES, (GQ_SMEM_LIMIT - fx) / GQ_STAGE);
+    c.smem = fx + (size_t)c.stages * GQ_STAGE;
+    found = true;
+  }
+  if (!found) c.ok = false;
+  return c;
+}
+
+ScorePlan gq_plan(int B, int M, int sms) {
+  static const int forced = [] { const char* e = std::getenv("LGX_SCORE_SPLITS"); return e ? std::atoi(e) : 0; }();
+  static const double c0 = [] { const char* e = std::getenv("LGX_SCORE_UNIT_OVERHEAD"); return e ? std::atof(e) : 14.0; }();
+  ScorePlan p = plan_score_waves(B, M, GQ_TILE_U, GQ_TILE_I, sms, c0);
+  if (forced > 0) {
+    const int r = std::max(1, std::min(forced, std::min(p.n_item_tiles, kMaxSplits)));
+    p.tiles_per_split = (p.n_item_tiles + r - 1) / r;
+    p.n_splits = (p.n_item_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  }
+  return p;
+}
+
+template <int KMAX, bool SMALLQ, bool SHARE>
+static int gq_launch2(dim3 grid, const GqConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
+                      const GqParams& p, cudaStream_t st) {
+  static bool configured[kMaxDevices] = {};       // the opt-in is a per-device function attribute
+  const int dev = current_device();
+  if (dev >= kMaxDevices || !configured[dev]) {
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_gq<KMAX, SMALLQ, SHARE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM_LIMIT));
+    if (dev < kMaxDevices) configured[dev] = true;
+  }
+  k_score_topk_gq<KMAX, SMALLQ, SHARE><<<grid, GQ_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  LGX_CHECK_LAUNCH();
+  return LGX_OK;
+}
+
+template <int KMAX, bool SMALLQ>
+static int gq_launch(dim3 grid, const GqConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
+                     const GqParams& p, cudaStream_t st) {
+  return p.row_bound ? gq_launch2<KMAX, SMALLQ, true>(grid, cfg, tm_u, tm_i, p, st)
+                     : gq_launch2<KMAX, SMALLQ, false>(grid, cfg, tm_u, tm_i, p, st);
+}
+
+int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, int B, const void* I_op, int M, int d,
+                  int K, int mode, int64_t item_offset, int64_t* out_idx, float* out_val, void* workspace,
+                  cudaStream_t st) {
+  const GqConfig cfg = gq_config(d, K, mode);
+  if (!cfg.ok) {
+    set_error("tcgen05 scoring needs d % 64 == 0, k <= 32 and 3*d <= 384 (bf16x3) / d <= 256 (bf16); "
+              "use LGX_SCORE_FP32 otherwise");
+    return LGX_ERR_INVALID;
+  }
+  const int ktot = cfg.k_blocks * GQ_KBLK;
+  CUtensorMap tm_u, tm_i;
+  int rc = make_operand_map(&tm_u, U_op, B, ktot, GQ_TILE_U);
+  if (rc != LGX_OK) return rc;
+  rc = make_operand_map(&tm_i, I_op, M, ktot, GQ_TILE_I);
+  if (rc != LGX_OK) return rc;
+  const ScorePlan plan = gq_plan(B, M, sm_count());
+  GqParams p;
+  p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages; p.q_cap = cfg.q_cap;
+  p.union_bound = cfg.union_bound;
+  p.n_splits = plan.n_splits; p.tiles_per_split = plan.tiles_per_split; p.item_offset = item_offset;
+  p.mask = make_mask(g); p.users = users;
+  {
+    const char* e = std::getenv("LGX_GQ_DEBUG");
+    p.dbg = e ? std::atoi(e) : 0;
+  }
+  p.has_mask = (g != nullptr && !(p.dbg & 4)) ? 1 : 0;
+  p.ws_val = reinterpret_cast<float*>(workspace);
+  p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
+  p.row_bound = nullptr;
+  if (plan.n_splits > 1) {
+    p.row_bound = reinterpret_cast<unsigned*>(p.ws_idx + (size_t)plan.n_splits * B * K);
+    LGX_CHECK_CUDA(cudaMemsetAsync(p.row_bound, 0, (size_t)B * sizeof(unsigned), st));
+  }
+  // ---- train-mask buckets (stream-ordered scratch from the device's memory pool: no sync, reused across calls)
+  p.mk_region = nullptr; p.mk_ptr = nullptr; p.mk_entries = nullptr;
+  void* mk_scratch = nullptr;
+  const int n_tiles = plan.n_item_tiles;
+  const size_t bucket_smem = (size_t)(n_tiles + 1) * sizeof(int);
+  if (p.has_mask && bucket_smem <= 200 * 1024 && !(p.dbg & 32)) {
+    static bool pool_ready[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < kMaxDevices && !pool_ready[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;                   // keep freed blocks in the pool instead of returning them to the OS
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      pool_ready[dev] = true;
+    }
+    // entries: every train item of the batch rows once.  Sized for 4x the graph's mean user degree (never more than
+    // the whole graph); a user tile that does not fit falls back to walking its lists inside the scoring kernel.
+    const double avg = (double)g->nnz * 0.5 / (double)std::max(1, g->n_users);
+    const unsigned long long cap = (unsigned long long)std::min<double>((double)g->nnz, 4.0 * avg * B + (1 << 20));
+    const size_t off_region = 256;
+    const size_t off_ptr = off_region + ((sizeof(int64_t) * plan.n_user_tiles + 255) & ~(size_t)255);
+    const size_t off_ent = off_ptr + ((sizeof(int32_t) * (size_t)plan.n_user_tiles * (n_tiles + 1) + 255) & ~(size_t)255);
+    const size_t total = off_ent + sizeof(uint16_t) * cap + 256;
+    LGX_CHECK_CUDA(cudaMallocAsync(&mk_scratch, total, st));
+    unsigned char* base = reinterpret_cast<unsigned char*>(mk_scratch);
+    LGX_CHECK_CUDA(cudaMemsetAsync(base, 0, 256, st));
+    GqBucketParams bp;
+    bp.mask = p.mask; bp.mask.m_items_hint = g->m_items; bp.users = users; bp.B = B; bp.M = M; bp.n_tiles = n_tiles; bp.item_offset = item_offset;
+    bp.cursor = reinterpret_cast<unsigned long long*>(base);
+    bp.cap = cap;
+    bp.region = reinterpret_cast<int64_t*>(base + off_region);
+    bp.ptr = reinterpret_cast<int32_t*>(base + off_ptr);
+    bp.entries = reinterpret_cast<uint16_t*>(base + off_ent);
+    if (bucket_smem > 40 * 1024) {
+      static size_t configured[kMaxDevices] = {};
+      if (dev >= kMaxDevices || bucket_smem > configured[dev]) {
+        LGX_CHECK_CUDA(cudaFuncSetAttribute(k_mask_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev < kMaxDevices) configured[dev] = 200 * 1024;
+      }
+    }
+    k_mask_buckets<<<plan.n_user_tiles, MB_THREADS, bucket_smem, st>>>(bp);
+    LGX_CHECK_LAUNCH();
+    p.mk_region = bp.region; p.mk_ptr = bp.ptr; p.mk_entries = bp.entries;
+  }
+  dim3 grid(plan.n_user_tiles, plan.n_splits);
+  const bool smallq = cfg.q_cap < 32;
+  if (K <= 20 && !smallq) rc = gq_launch<20, false>(grid, cfg, tm_u, tm_i, p, st);
+  else if (K <= 20) rc = gq_launch<20, true>(grid, cfg, tm_u, tm_i, p, st);
+  else if (K <= 24 && !smallq) rc = gq_launch<24, false>(grid, cfg, tm_u, tm_i, p, st);
+  else if (K <= 24) rc = gq_launch<24, true>(grid, cfg, tm_u, tm_i, p, st);
+  else if (!smallq) rc = gq_launch<32, false>(grid, cfg, tm_u, tm_i, p, st);
+  else rc = gq_launch<32, true>(grid, cfg, tm_u, tm_i, p, st);
+  if (mk_scratch) LGX_CHECK_CUDA(cudaFreeAsync(mk_scratch, st));     // stream-ordered: after the scoring kernel
+  if (rc != LGX_OK) return rc;
+  GqRescoreParams rp;
+  rp.ws_val = p.ws_val; rp.ws_idx = p.ws_idx; rp.P = plan.n_splits; rp.B = B; rp.K = K; rp.M = M; rp.ktot = ktot;
+  rp.U_op = reinterpret_cast<const __nv_bfloat16*>(U_op); rp.I_op = reinterpret_cast<const __nv_bfloat16*>(I_op);
+  rp.mask = p.mask; rp.users = users; rp.item_offset = item_offset; rp.out_idx = out_idx; rp.out_val = out_val;
+  k_rescore_topk<<<(B + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, st>>>(rp);
+  LGX_CHECK_LAUNCH();
+  return LGX_OK;
+}
+
+}  // namespace lgx

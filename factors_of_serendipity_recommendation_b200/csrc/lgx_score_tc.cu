@@ -30,6 +30,7 @@
 #include "lgx_common.cuh"
 #include "lgx_score_plan.cuh"
 #include "lgx_topk.cuh"
+#include "lgx_tc_ptx.cuh"
 
 namespace lgx {
 
@@ -39,6 +40,19 @@ int launch_merge_i32(const float* ws_val, const int32_t* ws_idx, int P, int B, i
 TrainMask make_mask(const lgx_graph* g);
 int score_topk_fp32(const lgx_graph* g, const float* U, const int64_t* users, int B, const float* I, int M, int d,
                     int K, int64_t item_offset, int64_t* out_idx, float* out_val, void* workspace, cudaStream_t st);
+// the group-queue kernel (lgx_score_gq.cu): the default tcgen05 path
+struct GqConfig { int k_blocks, stages, q_cap, union_bound; size_t smem; bool ok; };
+GqConfig gq_config(int d, int K, int mode);
+ScorePlan gq_plan(int B, int M, int sms);
+int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, int B, const void* I_op, int M, int d,
+                  int K, int mode, int64_t item_offset, int64_t* out_idx, float* out_val, void* workspace,
+                  cudaStream_t st);
+// LGX_SCORE_KERNEL=2 selects the first tcgen05 kernel of this file (per-column candidates, mask cursor in the
+// epilogue) for A/B runs; the default is the group-queue kernel.
+static bool use_gq(int d, int K, int mode) {
+  static const int v = [] { const char* e = std::getenv("LGX_SCORE_KERNEL"); return e ? std::atoi(e) : 3; }();
+  return v != 2 && gq_config(d, K, mode).ok;
+}
 
 constexpr int TC_TILE_U = 128;                 // UMMA M
 constexpr int TC_KBLK = 64;                    // bf16 elements per K-block = one 128-byte swizzle row
@@ -63,101 +77,6 @@ struct TcGeo {
 };
 constexpr int TC_SMEM_LIMIT = 232448;          // 227 KB opt-in limit per CTA
 
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-// Bounded wait: a protocol bug traps instead of hanging the GPU (the clock is read every 1024 polls).
-// BACKOFF: the single-thread TMA / MMA warps sleep between polls -- their spin loops were 28% of all issued
-// instructions (ncu); time-neutral on B200 (2.345 vs 2.353 ms) but it frees issue slots and power.
-template <bool BACKOFF>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t polls = 0;
-  while (!mbar_try(bar, parity)) {
-    if (BACKOFF) __nanosleep(32);
-    if ((++polls & 1023u) == 0 && clock64() - t0 > 8000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
-  d |= (uint64_t)(1024u >> 4) << 32;           // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                      // layout type: SWIZZLE_128B
-  return d;
-}
-
-#define LGX_TMEM_LD32(v, taddr)                                                                          \
-  asm volatile(                                                                                          \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                          \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                          \
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"          \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),         \
-        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),       \
-        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),       \
-        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                            \
-      : "r"(taddr)                                                                                       \
-      : "memory")
-// The wait names the destination registers as in/out operands so the compiler cannot hoist their
-// uses above it (the values are only defined once the wait retires).
-#define LGX_TMEM_WAIT(v)                                                                                  \
-  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                           \
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),      \
-                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),  \
-                 "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]),            \
-                 "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]),            \
-                 "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])             \
-               :                                                                                          \
-               : "memory")
-
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
 
 struct TcParams {
   int B, M, K;            // users in batch, local items, top-K
@@ -581,7 +500,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // [rows, ktot] bf16 row-major -> boxes of [box_rows x 64] with the 128-byte swizzle
-static int make_operand_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int box_rows) {
+int make_operand_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LGX_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
@@ -661,11 +580,12 @@ static ScorePlan tc_plan(int B, int M, const TcConfig& cfg, int sms) {
 template <int KMAX, bool SMALLQ, int NSEG, bool SHARE>
 static int launch_tc2(dim3 grid, const TcConfig& cfg, const CUtensorMap& tm_u, const CUtensorMap& tm_i,
                      const TcParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};       // the opt-in is a per-device function attribute
+  const int dev = current_device();
+  if (dev >= kMaxDevices || !configured[dev]) {
     LGX_CHECK_CUDA(cudaFuncSetAttribute(k_score_topk_tc<KMAX, SMALLQ, NSEG, SHARE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    configured = true;
+    if (dev < kMaxDevices) configured[dev] = true;
   }
   k_score_topk_tc<KMAX, SMALLQ, NSEG, SHARE><<<grid, TcGeo<NSEG>::THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
   LGX_CHECK_LAUNCH();
@@ -684,6 +604,8 @@ static int launch_tc(dim3 grid, const TcConfig& cfg, const CUtensorMap& tm_u, co
 static int score_topk_tc(const lgx_graph* g, const void* U_op, const int64_t* users, int B, const void* I_op, int M,
                          int d, int K, int mode, int64_t item_offset, int64_t* out_idx, float* out_val,
                          void* workspace, cudaStream_t st) {
+  // the group-queue kernel where its shared-memory budget fits (everything but K = 3d = 384)
+  if (use_gq(d, K, mode)) return score_topk_gq(g, U_op, users, B, I_op, M, d, K, mode, item_offset, out_idx, out_val, workspace, st);
   const TcConfig cfg = tc_config(d, K, mode);
   if (!cfg.ok) {
     set_error("tcgen05 scoring needs d % 64 == 0, k <= 32 and the user tile + 2 item stages to fit in 227 KB "
@@ -735,6 +657,7 @@ size_t lgx_score_topk_workspace_bytes(int32_t B, int32_t M, int32_t d, int32_t k
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) sms = sm_count(); else cudaGetLastError();
   if (mode == LGX_SCORE_FP32) return (size_t)plan_score(B, M, 64, 64, sms, 4).n_splits * B * k * 8 + 256;
+  if (use_gq(d, k, mode)) return (size_t)gq_plan(B, M, sms).n_splits * B * k * 8 + (size_t)B * sizeof(unsigned) + 256;
   TcConfig cfg = tc_config(d, k, mode);
   if (!cfg.ok) cfg.tile_items = TcGeo<2>::TILE_I;
   const ScorePlan plan = tc_plan(B, M, cfg, sms);
@@ -752,6 +675,8 @@ int lgx_score_plan(int32_t B, int32_t M, int32_t d, int32_t k, int32_t mode, int
   ScorePlan plan;
   if (mode == LGX_SCORE_FP32) {
     plan = plan_score(B, M, 64, 64, sms, 4);
+  } else if (use_gq(d, k, mode)) {
+    plan = gq_plan(B, M, sms);
   } else {
     TcConfig cfg = tc_config(d, k, mode);
     if (!cfg.ok) cfg.tile_items = TcGeo<2>::TILE_I;

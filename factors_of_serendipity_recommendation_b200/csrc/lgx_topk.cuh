@@ -15,6 +15,7 @@ struct TrainMask {
   const int64_t* indptr;   // NULL = no mask
   const int32_t* indices;
   int32_t n_users;
+  int32_t m_items_hint;    // catalogue size when the caller knows it (0 = unknown); only used to skip range searches
   __device__ __forceinline__ bool contains(int64_t user, int64_t item) const {
     if (indptr == nullptr || user < 0) return false;
     int64_t lo = indptr[user], hi = indptr[user + 1];

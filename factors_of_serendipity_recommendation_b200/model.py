@@ -96,6 +96,35 @@ def _as_index(t, device):
     return t.to(device=device, dtype=torch.int64).contiguous()
 
 
+def tc_mode_for(mode_id: int, d: int, k: int) -> int:
+    """The tcgen05 tile covers d % 64 == 0, k <= 32, d <= 256 (bf16) / 128 (bf16x3); every other shape runs the exact
+    fp32 CUDA-core kernel (about 15x slower per score -- a warning is printed once per shape)."""
+    if mode_id != _lgx.SCORE_FP32 and (d % 64 != 0 or k > 32 or (mode_id == _lgx.SCORE_BF16X3 and d > 128) or d > 256):
+        key = (mode_id, d, k)
+        if key not in _warned_fp32:
+            _warned_fp32.add(key)
+            world.cprint(f"[lgx] scoring d={d}, k={k} is outside the tensor-core tile (d % 64 == 0, k <= 32, d <= 256): "
+                         "using the fp32 CUDA-core kernel (~15x slower per score)")
+        return _lgx.SCORE_FP32
+    return mode_id
+
+
+_warned_fp32 = set()
+
+
+def fused_topk(graph, all_users, all_items, users, k: int, mode_id: int, packed_items=None):
+    """score + train mask (graph's user rows, or None) + top-k for the batch `users` -> (idx, val, packed item operand)."""
+    d = all_items.shape[1]
+    mode_id = tc_mode_for(mode_id, d, k)
+    if mode_id == _lgx.SCORE_FP32:
+        U_op, I_op = all_users.index_select(0, users), all_items
+    else:
+        I_op = packed_items if packed_items is not None else _lgx.pack_operand(all_items, None, mode_id, True)
+        U_op = _lgx.pack_operand(all_users, users, mode_id, False)
+    idx, val = _lgx.score_topk(graph, U_op, users, I_op, d, k, mode_id)
+    return idx, val, (I_op if mode_id != _lgx.SCORE_FP32 else None), mode_id
+
+
 class PureMF(BasicModel):
     """PT/model.py:41-84; scoring runs on the same kernels (no graph)."""
 
@@ -107,12 +136,33 @@ class PureMF(BasicModel):
         self.f = nn.Sigmoid()
         self.embedding_user = nn.Embedding(self.num_users, self.latent_dim)   # N(0,1) default init, PT/model.py:52-57
         self.embedding_item = nn.Embedding(self.num_items, self.latent_dim)
+        object.__setattr__(self, "_dataset", dataset)      # not a submodule / not in the state_dict
 
     def getUsersRating(self, users):
         users = _as_index(users, self.embedding_user.weight.device)
         with torch.no_grad():
             return _lgx.score_dense(self.embedding_user.weight.detach().contiguous(), users,
                                     self.embedding_item.weight.detach().contiguous(), apply_sigmoid=True)
+
+    def topk(self, users, k: int, exclude_train: bool = True, mode: str | None = None, sigmoid: bool = False):
+        """Fused getUsersRating + train mask + torch.topk (PT/Procedure.py:127-135) so Procedure.Test serves the MF
+        baseline too (the reference's Test only needs getUsersRating, PT/Procedure.py:126)."""
+        dev = self.embedding_user.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("PureMF (B200 engine) must be on a CUDA device: there is no CPU path")
+        graph = None
+        if exclude_train:
+            if self._dataset is None or not hasattr(self._dataset, "getGraphHandle"):
+                raise RuntimeError("PureMF.topk(exclude_train=True) needs a dataset with getGraphHandle()")
+            graph = self._dataset.getGraphHandle()
+        with torch.no_grad():
+            users = _as_index(users, dev)
+            idx, val, _, _ = fused_topk(graph, self.embedding_user.weight.detach().contiguous(),
+                                        self.embedding_item.weight.detach().contiguous(), users, k,
+                                        _lgx.MODES[mode or "bf16x3"])
+            if sigmoid:
+                val = torch.where(val == -1024.0, val, torch.sigmoid(val))
+            return idx, val
 
     def bpr_loss(self, users, pos, neg):
         users_emb = self.embedding_user(users.long())
@@ -268,21 +318,12 @@ class LightGCN(BasicModel):
         with torch.no_grad():
             all_users, all_items = self.computer()
             users = _as_index(users, all_users.device)
-            d = self.latent_dim
-            if mode_id != _lgx.SCORE_FP32 and (d % 64 != 0 or k > 32 or (mode_id == _lgx.SCORE_BF16X3 and d > 128)
-                                               or d > 256):
-                mode_id = _lgx.SCORE_FP32      # shapes the tensor-core tile does not cover run on CUDA cores
-            if mode_id == _lgx.SCORE_FP32:
-                U_op = all_users.index_select(0, users)
-                I_op = all_items
-            else:
-                key = (self._weights_key(), mode_id)
-                I_op = self._packed.get(key)
-                if I_op is None:
-                    self._packed = {key: _lgx.pack_operand(all_items, None, mode_id, True)}
-                    I_op = self._packed[key]
-                U_op = _lgx.pack_operand(all_users, users, mode_id, False)
-            idx, val = _lgx.score_topk(self.graph if exclude_train else None, U_op, users, I_op, d, k, mode_id)
+            mode_id = tc_mode_for(mode_id, self.latent_dim, k)
+            key = (self._weights_key(), mode_id)
+            idx, val, packed, _ = fused_topk(self.graph if exclude_train else None, all_users, all_items, users, k, mode_id,
+                                             packed_items=self._packed.get(key))
+            if packed is not None and key not in self._packed:
+                self._packed = {key: packed}
             if sigmoid:
                 val = torch.where(val == -1024.0, val, torch.sigmoid(val))
             return idx, val

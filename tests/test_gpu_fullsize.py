@@ -1,0 +1,109 @@
+"""Parity at the BENCHMARKED sizes (GPU): the launches bench.py times, checked on sampled rows.
+
+* Amazon-Book shape (52 643 x 91 599, d = 64): the unsplit 412 x 358-tile scoring pass exactly as bench.py issues it
+  (bf16 and bf16x3), 512 sampled users against fp64 CPU scores of the same propagated embeddings with the users'
+  train items masked -- "identical up to ties" with the tolerance north_star states (1e-2 bf16, 1e-5 bf16x3).
+* one configs[4] shard: 4096 users x 250 000 items, d = 64 / 128 / 256, split over several CTAs per user tile
+  (bounds shared through global memory), no mask.
+* one synth-10m-shape propagation layer: 256 sampled output rows against a CPU gather of those rows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lightgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_rows(scores64, idx, val, k, tol_rel):
+    """scores64: fp64 [rows, M] with masked items at -inf."""
+    scale = np.abs(scores64[np.isfinite(scores64)]).max()
+    for r in range(scores64.shape[0]):
+        assert O.topk_is_valid(scores64[r], idx[r], k, tol=tol_rel * scale), f"row {r} violates the top-{k} contract"
+        got = scores64[r, idx[r]]
+        assert np.all(np.isfinite(got)), "a masked train item was returned"
+        assert np.all(np.diff(val[r]) <= 0)
+        assert np.abs(val[r] - got).max() <= 4 * max(tol_rel, 2e-6) * scale + 1e-6
+
+
+@pytest.fixture(scope="module")
+def amazon():
+    from factors_of_serendipity_recommendation_b200 import dataloader, model, synth, world
+    nu, mi, E, d = synth.SHAPES["amazon-book"]
+    u, i = synth.make_interactions(nu, mi, E, seed=2020)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=2020)
+    cfg = dict(world.config)
+    cfg.update(lightGCN_n_layers=3, latent_dim_rec=d, pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy())
+    ds = dataloader.InteractionDataset(nu, mi, u, i, device="cuda")
+    m = model.LightGCN(cfg, ds).cuda().eval()
+    return dict(nu=nu, mi=mi, d=d, u=u, i=i, model=m, ds=ds)
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16", 1e-2), ("bf16x3", 1e-5)])
+def test_amazon_book_pass_as_benchmarked(amazon, mode, tol):
+    from factors_of_serendipity_recommendation_b200 import _lgx
+    nu, mi, d, m, ds = amazon["nu"], amazon["mi"], amazon["d"], amazon["model"], amazon["ds"]
+    g = ds.getGraphHandle()
+    mode_id = _lgx.MODES[mode]
+    all_users = torch.arange(nu, dtype=torch.int64, device="cuda")
+    with torch.no_grad():
+        au, ai = m.computer()
+    I_op = _lgx.pack_operand(ai, None, mode_id, True)
+    U_op = _lgx.pack_operand(au, all_users, mode_id, False)
+    plan = _lgx.score_plan(nu, mi, d, 20, mode_id)
+    assert plan["user_tiles"] == 412 and plan["item_tiles"] == 358
+    idx, val = _lgx.score_topk(g, U_op, all_users, I_op, d, 20, mode_id)      # the launch bench.py times
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    assert idx.min() >= 0 and idx.max() < mi
+    rng = np.random.default_rng(7)
+    rows = np.unique(np.concatenate([rng.choice(nu, 500, replace=False), [0, 1, 127, 128, nu - 2, nu - 1],
+                                     np.argsort(-np.bincount(amazon["u"], minlength=nu))[:6]]))   # + the heaviest users
+    s = au[torch.from_numpy(rows).cuda()].double().cpu().numpy() @ ai.double().cpu().numpy().T
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(amazon["u"], minlength=nu))])
+    for r, uid in enumerate(rows):
+        s[r, amazon["i"][indptr[uid]:indptr[uid + 1]]] = -np.inf                 # interactions are sorted by (user, item)
+    _check_rows(s, idx[rows], val[rows], 20, tol)
+
+
+@pytest.mark.parametrize("d", [64, 128, 256])
+def test_config5_shard_shape(d):
+    """4096-user batch x one 250 K-item shard of the 2 M catalogue: several CTAs per user tile share row bounds."""
+    from factors_of_serendipity_recommendation_b200 import _lgx
+    B, M, k = 4096, 250_000, 20
+    g = torch.Generator(device="cuda").manual_seed(d)
+    U = torch.empty(B, d, device="cuda").normal_(std=0.1, generator=g)
+    I = torch.empty(M, d, device="cuda").normal_(std=0.1, generator=g)
+    I *= torch.empty(M, 1, device="cuda").uniform_(0.5, 2.0, generator=g)
+    Up = _lgx.pack_operand(U, None, _lgx.SCORE_BF16, False)
+    Ip = _lgx.pack_operand(I, None, _lgx.SCORE_BF16, True)
+    plan = _lgx.score_plan(B, M, d, k, _lgx.SCORE_BF16)
+    assert plan["splits"] > 1
+    idx, val = _lgx.score_topk(None, Up, None, Ip, d, k, _lgx.SCORE_BF16, item_offset=500_000)
+    idx, val = idx.cpu().numpy() - 500_000, val.cpu().numpy()
+    rows = np.random.default_rng(d).choice(B, 192, replace=False)
+    s = (U[torch.from_numpy(rows).cuda()].double() @ I.double().T).cpu().numpy()
+    _check_rows(s, idx[rows], val[rows], k, 1e-2)
+
+
+def test_synth10m_layer_sampled_rows():
+    """One propagation layer at d = 128 on a 10 M-edge graph: sampled rows == CPU gather (<= 1e-5 relative)."""
+    from factors_of_serendipity_recommendation_b200 import _lgx, synth
+    nu, mi, E, d = synth.SHAPES["synth-10m"]
+    u, i = synth.make_interactions_device(nu, mi, E, seed=2020, device="cuda")
+    g = _lgx.Graph.build(nu, mi, u, i)
+    N = g.n_rows
+    X = torch.empty(N, d, device="cuda").normal_(std=0.1, generator=torch.Generator(device="cuda").manual_seed(1))
+    Y = torch.empty_like(X)
+    g.spmm(X, Y=Y)
+    e = g.export()
+    indptr, indices, values = e["indptr"].cpu().numpy(), e["indices"].cpu().numpy(), e["values"].cpu().numpy()
+    Xc = X.cpu().numpy().astype(np.float64)
+    order = e["row_order"].cpu().numpy()
+    rows = np.unique(np.concatenate([np.random.default_rng(3).choice(N, 250, replace=False), order[:3], order[-3:]]))
+    Yc = Y.cpu().numpy()
+    for r in rows:
+        lo, hi = indptr[r], indptr[r + 1]
+        ref = (values[lo:hi].astype(np.float64)[:, None] * Xc[indices[lo:hi]]).sum(0)
+        scale = np.abs(values[lo:hi].astype(np.float64)[:, None] * Xc[indices[lo:hi]]).sum(0).max() + 1e-30
+        assert np.abs(Yc[r] - ref).max() <= 1e-5 * scale, r

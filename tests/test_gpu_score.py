@@ -200,33 +200,44 @@ def test_k_range(k, mode):
     assert all(O.topk_is_valid(s_nomask[r], idx2[r].cpu().numpy(), k, tol=tol * scale) for r in range(nu))
 
 
-def test_twelve_warp_variant_matches_default():
-    """LGX_SCORE_NSEG=3 (192-column tiles, 12 epilogue warps; opt-in A/B variant) returns the same top-K as the
-    default kernel.  The switch is read once per process, so the variant runs in a child interpreter."""
+def test_group_queue_kernel_matches_first_tcgen05_kernel():
+    """The default group-queue kernel (lgx_score_gq.cu: tensor-core mask, top-K groups, rescoring) and the first
+    tcgen05 kernel (LGX_SCORE_KERNEL=2: per-column candidates, mask cursor in the epilogue) return the same top-K
+    up to ties / last-bit value differences (sequential fp32 rescoring vs the tensor core's summation order).
+    The switch is read once per process, so each kernel runs in a child interpreter."""
     import os
     import subprocess
     import sys
+    import tempfile
     code = r"""
 import numpy as np, torch
-from factors_of_serendipity_recommendation_b200 import _lgx
-g = torch.Generator().manual_seed(5)
-B, M, d = 300, 3 * 192 + 50, 64
-U = torch.randn(B, d, generator=g).cuda(); I = torch.randn(M, d, generator=g).cuda()
+from factors_of_serendipity_recommendation_b200 import _lgx, synth
+nu, mi, d = 300, 3 * 256 + 50, 64
+u, i = synth.make_interactions(nu, mi, 9000, seed=5)
+g = _lgx.Graph.build(nu, mi, torch.from_numpy(u), torch.from_numpy(i))
+gen = torch.Generator().manual_seed(5)
+U = torch.randn(nu, d, generator=gen).cuda(); I = torch.randn(mi, d, generator=gen).cuda()
+users = torch.arange(nu).cuda()
 out = {}
-Up = _lgx.pack_operand(U, None, _lgx.SCORE_BF16, False); Ip = _lgx.pack_operand(I, None, _lgx.SCORE_BF16, True)
-for k in (20, 24):
-    idx, val = _lgx.score_topk(None, Up, None, Ip, d, k, _lgx.SCORE_BF16)
-    out[f"i{k}"] = idx.cpu().numpy(); out[f"v{k}"] = val.cpu().numpy()
+for mode in (_lgx.SCORE_BF16, _lgx.SCORE_BF16X3):
+    Up = _lgx.pack_operand(U, None, mode, False); Ip = _lgx.pack_operand(I, None, mode, True)
+    for k in (1, 20, 24, 32):
+        idx, val = _lgx.score_topk(g, Up, users, Ip, d, k, mode)
+        out[f"i{mode}_{k}"] = idx.cpu().numpy(); out[f"v{mode}_{k}"] = val.cpu().numpy()
 np.savez(__import__("sys").argv[1], **out)
 """
-    import tempfile
     res = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for nseg in ("2", "3"):
-            path = os.path.join(tmp, f"o{nseg}.npz")
-            env = dict(os.environ, LGX_SCORE_NSEG=nseg)
+        for kern in ("2", "3"):
+            path = os.path.join(tmp, f"o{kern}.npz")
+            env = dict(os.environ, LGX_SCORE_KERNEL=kern)
             subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-            res[nseg] = dict(np.load(path))
+            res[kern] = dict(np.load(path))
     for key in res["2"]:
-        assert np.array_equal(res["2"][key], res["3"][key]), key
+        a, b = res["2"][key], res["3"][key]
+        if key.startswith("i"):
+            same = sum(set(x.tolist()) == set(y.tolist()) for x, y in zip(a, b))
+            assert same >= len(a) - 1, (key, same)
+        else:
+            assert np.allclose(a, b, rtol=2e-5, atol=2e-5), key
