@@ -97,4 +97,24 @@ struct lgx_graph {
   lgx::WorkItem* work = nullptr; // [n_work]
   lgx::LongRow* long_rows = nullptr;  // [n_long]
   int32_t* tpos = nullptr;            // [nnz] position of the mirrored entry (built on demand for dropout)
+  // Hot columns (the embedding rows gathered most often), for the shared-memory staging of the SpMM:
+  //   hot_ids   [n_hot] column ids by descending gather count (built with the graph; NULL = not built: huge graphs)
+  //   hot_count host prefix sums: hot_cover[j] = gathers that hit the top kHotSteps[j] columns
+  //   hot_idx / hot_val / hot_work: every work unit's entries re-ordered hot-first for a table of the hot_h hottest
+  //             columns -- [n_hot table slots][cold column ids], values alongside, work items with len | n_hot << 16
+  //             (built on first use for the table size that fits the embedding width; rebuilt if another width asks
+  //             for another size)
+  int32_t* hot_ids = nullptr;
+  int32_t n_hot = 0;
+  int64_t hot_cover[6] = {0, 0, 0, 0, 0, 0};
+  mutable int32_t* hot_idx = nullptr;
+  mutable float* hot_val = nullptr;
+  mutable lgx::WorkItem* hot_work = nullptr;
+  mutable int32_t hot_h = 0;
 };
+namespace lgx {
+constexpr int kHotMax = 3072;                                           // 192 KB of fp32 rows at d = 16
+constexpr int kHotSteps[6] = {96, 192, 384, 768, 1536, 3072};           // table sizes for d = 512 ... 16
+int build_hot_columns(lgx_graph* g, cudaStream_t st);                   // lgx_graph.cu
+int ensure_hot_index(const lgx_graph* g, int h, cudaStream_t st);       // lgx_graph.cu; builds g->hot_idx for table size h
+}

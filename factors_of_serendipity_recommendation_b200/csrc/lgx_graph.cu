@@ -9,6 +9,10 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include <mutex>
 #include <vector>
 
 #include "lgx_common.cuh"
@@ -201,6 +205,7 @@ static void free_graph(lgx_graph* g) {
   if (!g) return;
   cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->values); cudaFree(g->degree);
   cudaFree(g->dinv); cudaFree(g->row_order); cudaFree(g->work); cudaFree(g->long_rows); cudaFree(g->tpos);
+  cudaFree(g->hot_ids); cudaFree(g->hot_idx); cudaFree(g->hot_val); cudaFree(g->hot_work);
   delete g;
 }
 
@@ -270,6 +275,134 @@ static int build_schedule(lgx_graph* g, int32_t chunk_nnz, cudaStream_t st) {
 #undef SCHED_CUDA
   cleanup();
   return rc;
+}
+
+// ---------------------------------------------------------------------------------- hot columns
+// The SpMM gathers X[col] once per stored entry, so "hot" = most frequent column.  For the square symmetric A_hat
+// that is the row degree, but a row shard (n_rows < n_cols) has its own column statistics: count them.
+__global__ void k_col_hist(const int32_t* __restrict__ indices, int64_t nnz, uint32_t* __restrict__ cnt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) atomicAdd(&cnt[indices[k]], 1u);
+}
+__global__ void k_iota(int32_t* __restrict__ a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)i;
+}
+__global__ void k_hot_rank(const int32_t* __restrict__ hot_ids, int h, int32_t* __restrict__ rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < h) rank[hot_ids[i]] = i;
+}
+// One warp per work unit: entries whose column has a table slot go first (as the slot), the rest keep their column id;
+// both parts keep their original relative order.
+__global__ void __launch_bounds__(256)
+k_hot_reorder(const WorkItem* __restrict__ work, int64_t n_work, const int32_t* __restrict__ indices,
+              const float* __restrict__ values, const int32_t* __restrict__ rank, int32_t* __restrict__ hot_idx,
+              float* __restrict__ hot_val, WorkItem* __restrict__ hot_work) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_work) return;
+  const WorkItem it = work[w];
+  const unsigned lt = (1u << lane) - 1u;
+  int n_hot = 0;
+  for (int base = 0; base < it.len; base += 32) {
+    const bool hot = base + lane < it.len && rank[indices[it.start + base + lane]] >= 0;
+    n_hot += __popc(__ballot_sync(0xffffffffu, hot));
+  }
+  int ph = 0, pc = n_hot;
+  for (int base = 0; base < it.len; base += 32) {
+    const bool in = base + lane < it.len;
+    int32_t c = 0, r = -1;
+    float v = 0.f;
+    if (in) { c = indices[it.start + base + lane]; v = values[it.start + base + lane]; r = rank[c]; }
+    const unsigned hm = __ballot_sync(0xffffffffu, in && r >= 0), cm = __ballot_sync(0xffffffffu, in && r < 0);
+    if (in) {
+      const int pos = r >= 0 ? ph + __popc(hm & lt) : pc + __popc(cm & lt);
+      hot_idx[it.start + pos] = r >= 0 ? r : c;
+      hot_val[it.start + pos] = v;
+    }
+    ph += __popc(hm);
+    pc += __popc(cm);
+  }
+  if (lane == 0) {
+    WorkItem o = it;
+    o.len = it.len | (n_hot << 16);
+    hot_work[w] = o;
+  }
+}
+
+int build_hot_columns(lgx_graph* g, cudaStream_t st) {
+  // opt-in (see hot_table_rows in lgx_spmm.cu); not for graphs where the re-ordered copies would cost GBs
+  static const int enabled = [] { const char* e = std::getenv("LGX_SPMM_HOT"); return e ? std::atoi(e) : 0; }();
+  if (enabled != 1) return LGX_OK;
+  if (g->nnz == 0 || g->nnz > ((int64_t)1 << 28) || g->n_cols < 2 * kHotMax) return LGX_OK;
+  const int64_t n = g->n_cols;
+  uint32_t *cnt = nullptr, *cnt_sorted = nullptr;
+  int32_t *iota = nullptr, *ids_sorted = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(cnt); cudaFree(cnt_sorted); cudaFree(iota); cudaFree(ids_sorted); cudaFree(tmp); };
+#define HOT_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                 \
+      cleanup();                                                                            \
+      return LGX_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+  HOT_CUDA(cudaMalloc(&cnt, sizeof(uint32_t) * n));
+  HOT_CUDA(cudaMalloc(&cnt_sorted, sizeof(uint32_t) * n));
+  HOT_CUDA(cudaMalloc(&iota, sizeof(int32_t) * n));
+  HOT_CUDA(cudaMalloc(&ids_sorted, sizeof(int32_t) * n));
+  HOT_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * n, st));
+  k_col_hist<<<grid_for(g->nnz, 256), 256, 0, st>>>(g->indices, g->nnz, cnt);
+  k_iota<<<grid_exact(n, 256), 256, 0, st>>>(iota, n);
+  size_t tb = 0;
+  HOT_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, cnt, cnt_sorted, iota, ids_sorted, n, 0, 32, st));
+  HOT_CUDA(cudaMalloc(&tmp, tb + 16));
+  HOT_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, cnt, cnt_sorted, iota, ids_sorted, n, 0, 32, st));
+  const int h = (int)std::min<int64_t>(kHotMax, n);
+  HOT_CUDA(cudaMalloc(&g->hot_ids, sizeof(int32_t) * h));
+  HOT_CUDA(cudaMemcpyAsync(g->hot_ids, ids_sorted, sizeof(int32_t) * h, cudaMemcpyDeviceToDevice, st));
+  std::vector<uint32_t> top(h);
+  HOT_CUDA(cudaMemcpyAsync(top.data(), cnt_sorted, sizeof(uint32_t) * h, cudaMemcpyDeviceToHost, st));
+  HOT_CUDA(cudaStreamSynchronize(st));
+#undef HOT_CUDA
+  g->n_hot = h;
+  int64_t acc = 0;
+  int j = 0;
+  for (int i = 0; i < h; ++i) {
+    acc += top[i];
+    while (j < 6 && i + 1 == kHotSteps[j]) g->hot_cover[j++] = acc;
+  }
+  for (; j < 6; ++j) g->hot_cover[j] = acc;
+  cleanup();
+  return LGX_OK;
+}
+
+// hot_idx for a table of the h hottest columns.  Serialised by a mutex: the first SpMM of a given width builds it.
+int ensure_hot_index(const lgx_graph* g, int h, cudaStream_t st) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (g->hot_idx != nullptr && g->hot_h == h) return LGX_OK;
+  if (g->hot_ids == nullptr || h > g->n_hot) { set_error("hot columns were not built for this graph"); return LGX_ERR_INVALID; }
+  int32_t* rank = nullptr;
+  LGX_CHECK_CUDA(cudaMalloc(&rank, sizeof(int32_t) * g->n_cols));
+  if (g->hot_idx == nullptr) {
+    cudaError_t e = cudaMalloc(&g->hot_idx, sizeof(int32_t) * g->nnz);
+    if (e == cudaSuccess) e = cudaMalloc(&g->hot_val, sizeof(float) * g->nnz);
+    if (e == cudaSuccess) e = cudaMalloc(&g->hot_work, sizeof(WorkItem) * std::max<int64_t>(1, g->n_work));
+    if (e != cudaSuccess) { cudaFree(rank); set_error("cudaMalloc(hot arrays) failed"); return LGX_ERR_CUDA; }
+  }
+  cudaMemsetAsync(rank, 0xff, sizeof(int32_t) * g->n_cols, st);
+  k_hot_rank<<<grid_exact(h, 256), 256, 0, st>>>(g->hot_ids, h, rank);
+  if (g->n_work > 0)
+    k_hot_reorder<<<grid_exact(g->n_work * 32, 256), 256, 0, st>>>(g->work, g->n_work, g->indices, g->values, rank,
+                                                                  g->hot_idx, g->hot_val, g->hot_work);
+  cudaError_t e = cudaStreamSynchronize(st);      // one-time set-up; a width change mid-stream must not race the old index
+  cudaFree(rank);
+  if (e != cudaSuccess) { set_error(std::string("hot index build failed: ") + cudaGetErrorString(e)); return LGX_ERR_CUDA; }
+  g->hot_h = h;
+  return LGX_OK;
 }
 
 }  // namespace lgx
@@ -381,6 +514,7 @@ int lgx_graph_build(int32_t n_users, int32_t m_items, int64_t n_edges, const int
 #undef BUILD_CUDA
   cleanup();
   int rc = build_schedule(g, chunk_nnz, st);
+  if (rc == LGX_OK) rc = build_hot_columns(g, st);
   if (rc != LGX_OK) {
     free_graph(g);
     return rc;
@@ -446,6 +580,7 @@ int lgx_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_
   CSR_CUDA(cudaGetLastError());
 #undef CSR_CUDA
   int rc = build_schedule(g, chunk_nnz, st);
+  if (rc == LGX_OK) rc = build_hot_columns(g, st);
   if (rc != LGX_OK) {
     free_graph(g);
     return rc;

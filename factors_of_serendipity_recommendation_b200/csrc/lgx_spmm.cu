@@ -310,6 +310,114 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
   }
 }
 
+// Shared-memory staging of the hot rows (north_star: "shared-memory staging of hot rows").
+// On L2-resident graphs the kernel above is bound by the L2 -> SM gather path (1.53 GB of 256-byte row gathers per
+// Amazon-Book layer for 122 MB of algorithmic bytes, ~12 TB/s = the measured L2 ceiling), so the only way down is to
+// gather fewer bytes through L2.  One persistent CTA per SM (1024 threads = the same 32 warps as 4 x 256) copies the H
+// most frequently gathered embedding rows (H * d * 4 <= 192 KB; lgx_graph::hot_ids) into shared memory once per layer,
+// and the index stream it reads (lgx_graph::hot_idx) stores those columns as ~slot: such gathers are LDS.128 from the
+// table instead of LDG.128 through L2.  What it can save is the share of gathers that hit the table (hot_cover):
+// 23 % on the Amazon-Book shape (32 % of the item gathers, 12 % of the user gathers), nothing on graphs whose degree
+// mass is not concentrated -- the launcher uses it only above 10 % coverage.
+constexpr int HOT_THREADS = 1024;
+constexpr int HOT_SMEM_BYTES = 192 * 1024;
+// Every work unit's entries are stored hot-first (lgx_graph::hot_idx / hot_val / hot_work, built once per table
+// size): [n_hot table slots][len - n_hot cold column ids].  The unit is then two plain gather loops, LDS.128 from the
+// table and LDG.128 through L2 -- measured alternatives that mix the two per gather lost badly: a branch per gather
+// serialises the U gathers that must be in flight together (152 vs 125 us per Amazon-Book layer), a predicated
+// LDS/LDG pair per gather was worse still (374 us).
+template <int G, int V, int U>
+__global__ void __launch_bounds__(HOT_THREADS, 1)
+k_spmm_hot(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ hot_idx,
+           const float* __restrict__ hot_val, const float* __restrict__ X, const float* S_in,
+           float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div,
+           const int32_t* __restrict__ hot_ids, int H) {
+  constexpr int D4 = G * V;
+  constexpr int D = 4 * D4;
+  constexpr int UU = U > G ? G : U;
+  extern __shared__ float4 tab[];                     // [H][D4]
+  const float4* __restrict__ Xall = reinterpret_cast<const float4*>(X);
+  for (int i = threadIdx.x; i < H * D4; i += HOT_THREADS) {
+    const int slot = i / D4, q = i - slot * D4;
+    tab[i] = __ldg(Xall + ((uint32_t)__ldg(hot_ids + slot) * (uint32_t)D4 + (uint32_t)q));
+  }
+  __syncthreads();
+  const int lig = threadIdx.x & (G - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int64_t n_rounds = (n_work + n_groups - 1) / n_groups;
+  const float4* __restrict__ X4 = Xall + lig;
+  const float4* tabl = tab + lig;
+
+  for (int64_t round = 0; round < n_rounds; ++round) {
+    const int64_t item = round * n_groups + group;
+    const int32_t* ci = hot_idx;
+    const float* cv = hot_val;
+    int32_t row = 0, len = 0, n_hot = 0, part = -1;
+    const bool have = item < n_work;
+    if (have) {
+      const int4 w0 = __ldg(reinterpret_cast<const int4*>(work + item));   // start, row, len | n_hot << 16
+      const int64_t start = ((int64_t)(uint32_t)w0.x) | ((int64_t)w0.y << 32);
+      ci += start; cv += start;
+      row = w0.z; len = w0.w & 0xffff; n_hot = (int32_t)((uint32_t)w0.w >> 16);
+      part = item < n_partials ? (int32_t)item : -1;
+    }
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // two segments: [0, n_hot) from the table, [n_hot, len) through L2.  Beyond a segment's end lanes hold slot /
+    // column 0 with value 0: a harmless gather.
+#pragma unroll
+    for (int seg = 0; seg < 2; ++seg) {
+      const int s0 = seg == 0 ? 0 : n_hot, s1 = seg == 0 ? n_hot : len;
+      const int slen = s1 - s0;
+      int maxlen = slen;
+#pragma unroll
+      for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+      int32_t c_nxt = 0;
+      float a_nxt = 0.f;
+      if (lig < slen) { c_nxt = ld_stream_i32(ci + s0 + lig); a_nxt = ld_stream_f32(cv + s0 + lig); }
+      for (int base = 0; base < maxlen; base += G) {
+        const int32_t c = c_nxt;
+        const float a = a_nxt;
+        const int kn = base + G + lig;
+        c_nxt = 0; a_nxt = 0.f;
+        if (kn < slen) { c_nxt = ld_stream_i32(ci + s0 + kn); a_nxt = ld_stream_f32(cv + s0 + kn); }
+        const int cnt = slen - base;
+        const bool full = __all_sync(0xffffffffu, cnt >= G);     // every group of the warp has a full batch: no checks
+#pragma unroll
+        for (int j0 = 0; j0 < G; j0 += UU) {
+          if (!full && __all_sync(0xffffffffu, cnt <= j0)) break;
+          float4 x[UU][V];
+          float av[UU];
+#pragma unroll
+          for (int j = 0; j < UU; ++j) {
+            const uint32_t cj = (uint32_t)__shfl_sync(0xffffffffu, c, j0 + j, G);
+            av[j] = __shfl_sync(0xffffffffu, a, j0 + j, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              if (seg == 0) x[j][v] = tabl[cj * (uint32_t)D4 + (uint32_t)(v * G)];
+              else x[j][v] = __ldg(X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G)));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < UU; ++j)
+#pragma unroll
+            for (int v = 0; v < V; ++v) fma4(acc[v], av[j], x[j][v]);
+        }
+      }
+    }
+    if (have) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int col = (lig + v * G) << 2;
+        if (part >= 0) *reinterpret_cast<float4*>(partial + (int64_t)part * D + col) = acc[v];
+        else epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
+      }
+    }
+  }
+}
+
 // d not a multiple of 4: scalar lanes (rare; the reference allows any --recdim).
 __global__ void __launch_bounds__(256)
 k_spmm_scalar(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
@@ -445,6 +553,46 @@ static void launch_fixed(const lgx_graph* g, const float* X, const float* S_in, 
   else launch_fixed_t<G, V, U, MINB, 3>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
 }
 
+// Table size for width d.  OPT-IN (LGX_SPMM_HOT=1, read at graph build and here): measured on B200 at the Amazon-Book
+// shape the staged kernel is SLOWER than the plain one -- 139 us per layer (table 192 KB; 137 / 135 us with 96 / 48 KB)
+// against 125 us -- although 23 % of its gathers are served from shared memory: the plain kernel is bound by
+// instruction issue and L2 latency per gather, not by L2 bytes, and the two-segment unit loop adds a ragged batch
+// and the persistent 1024-thread CTA loses the 4 x 256 launch's finer tail.  Kept for graphs with a heavier head.
+static int hot_table_rows(const lgx_graph* g, int d) {
+  if (!g->hot_ids || (d != 64 && d != 128) || g->chunk_nnz > 32767) return 0;
+  static const int forced = [] { const char* e = getenv("LGX_SPMM_HOT"); return e ? atoi(e) : 0; }();
+  if (forced != 1) return 0;
+  static const int budget = [] { const char* e = getenv("LGX_SPMM_HOT_KB"); return e ? atoi(e) * 1024 : HOT_SMEM_BYTES; }();
+  int j = 0;
+  while (j < 5 && kHotSteps[j + 1] * d * 4 <= std::min(budget, HOT_SMEM_BYTES)) ++j;      // largest step that fits (192 KB)
+  const int h = std::min(kHotSteps[j], (int)g->n_hot);
+  if (h < kHotSteps[j]) return 0;
+  const double cover = g->nnz > 0 ? (double)g->hot_cover[j] / (double)g->nnz : 0.0;
+  (void)cover;
+  return h;
+}
+
+template <int G, int V, int U>
+static int launch_hot(const lgx_graph* g, int h, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
+                      float div, cudaStream_t st) {
+  const int rc = ensure_hot_index(g, h, st);
+  if (rc != LGX_OK) return rc;
+  constexpr int D = 4 * G * V;
+  const size_t smem = (size_t)h * D * sizeof(float);
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev >= kMaxDevices || !configured[dev]) {
+    LGX_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_hot<G, V, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, HOT_SMEM_BYTES));
+    if (dev < kMaxDevices) configured[dev] = true;
+  }
+  const int64_t groups_per_block = HOT_THREADS / G;
+  const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, sm_count()));
+  k_spmm_hot<G, V, U><<<blocks, HOT_THREADS, smem, st>>>(g->hot_work, g->n_work, g->n_partials, g->hot_idx, g->hot_val, X,
+                                                         S_in, Y, S_out, partial, div, g->hot_ids, h);
+  return LGX_OK;
+}
+
 static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float div,
                      int32_t d, void* workspace, cudaStream_t st, const PeerOut& po = PeerOut{},
                      const DropSpec& drop = DropSpec{}) {
@@ -461,6 +609,12 @@ static int spmm_impl(const lgx_graph* g, const float* X, const float* S_in, floa
       const int64_t need = (g->n_work + 7) / 8;
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
       k_spmm_scalar<<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X, S_in, Y, S_out, partial, div, d, drop);
+    } else if (tuning().variant == 0 && po.n == 0 && !drop.enabled && fixed_ok && hot_table_rows(g, d) > 0) {
+      // hot rows staged in shared memory (plain propagation, forward and backward)
+      const int h = hot_table_rows(g, d);
+      const int rc = d == 64 ? launch_hot<16, 1, 4>(g, h, X, S_in, Y, S_out, partial, div, st)
+                             : launch_hot<32, 1, 4>(g, h, X, S_in, Y, S_out, partial, div, st);
+      if (rc != LGX_OK) return rc;
     } else if ((tuning().variant == 0 || po.n > 0) && fixed_ok) {
       // default: compile-time row stride, 4 gathers in flight per lane, >= 4 CTAs per SM
       // (B200 sweep over U x occupancy at Amazon-Book shape: profiles/r1_spmm_sweep.txt)

@@ -72,6 +72,25 @@ def merge_candidates_reference(cand_idx: torch.Tensor, cand_val: torch.Tensor, k
     return torch.gather(idx, 1, order)[:, :k], torch.gather(val, 1, order)[:, :k]
 
 
+def pack_candidates(idx: torch.Tensor, val: torch.Tensor) -> torch.Tensor:
+    """[.., k] int64 ids + fp32 scores -> one int32 tensor [.., 2k] (ids | score bits): item ids fit 31 bits, so
+    the exchange is one collective of 8 bytes per candidate instead of two of 8 + 4."""
+    return torch.cat([idx.to(torch.int32), val.contiguous().view(torch.int32)], dim=-1).contiguous()
+
+
+def unpack_candidates(buf: torch.Tensor):
+    k = buf.shape[-1] // 2
+    return buf[..., :k].to(torch.int64).contiguous(), buf[..., k:].contiguous().view(torch.float32)
+
+
+def gather_packed(idx: torch.Tensor, val: torch.Tensor, world: int, group=None):
+    """all-gather of (idx, val) candidate lists in ONE collective -> ([world, ...], [world, ...])."""
+    mine = pack_candidates(idx, val)
+    out = torch.empty((world * mine.shape[0],) + tuple(mine.shape[1:]), dtype=torch.int32, device=mine.device)
+    dist.all_gather_into_tensor(out, mine, group=group)         # concatenation along dim 0 (gloo and nccl agree on it)
+    return unpack_candidates(out.view((world,) + tuple(mine.shape)))
+
+
 class ShardedEngine:
     """Forward propagation + full-catalogue top-K over ``world`` GPUs (one instance per rank)."""
 
@@ -99,6 +118,7 @@ class ShardedEngine:
             propagate = "replicated" if layer_bytes < (64 << 20) else ("fused" if d in (16, 32, 64, 128, 256) else "allgather")
         self.mode = propagate
         self.peers = None
+        self._last_light = None
         if self.mode == "replicated":
             return
         e = graph.export()
@@ -254,11 +274,8 @@ class ShardedEngine:
                     I_op = _lgx.pack_operand(ai.contiguous(), None, mode_id, True)
                 i2, v2 = _lgx.score_topk(self.g_full, U_op, mine, I_op, self.d, k, mode_id)
                 idx[: hi - lo], val[: hi - lo] = i2, v2
-            all_idx = torch.empty(self.world * per, k, dtype=torch.int64, device=self.dev)
-            all_val = torch.empty(self.world * per, k, dtype=torch.float32, device=self.dev)
-            dist.all_gather_into_tensor(all_idx, idx)
-            dist.all_gather_into_tensor(all_val, val)
-            return all_idx[:B], all_val[:B]
+            all_idx, all_val = gather_packed(idx, val, self.world)       # ONE collective: [per, k] (int32 id | fp32 bits)
+            return all_idx.reshape(self.world * per, k)[:B], all_val.reshape(self.world * per, k)[:B]
         shard_items = ai[self.lo:self.hi]
         kk = min(k, self.hi - self.lo)
         if mode_id == _lgx.SCORE_FP32:
@@ -272,14 +289,16 @@ class ShardedEngine:
             pad_v = torch.full((B, k), float("-inf"), device=self.dev)
             pad_i[:, :kk], pad_v[:, :kk] = idx, val
             idx, val = pad_i, pad_v
-        all_idx = torch.empty(self.world, B, k, dtype=torch.int64, device=self.dev)
-        all_val = torch.empty(self.world, B, k, dtype=torch.float32, device=self.dev)
-        dist.all_gather_into_tensor(all_idx, idx.contiguous())
-        dist.all_gather_into_tensor(all_val, val.contiguous())
+        all_idx, all_val = gather_packed(idx.contiguous(), val.contiguous(), self.world)
         return _lgx.topk_merge(all_idx, all_val)
+
+    def last_light(self):
+        """The propagated embeddings of the last step() (original node order, replicated) -- for parity checks."""
+        return self._last_light
 
     def step(self, E0, users, k, mode_id, events=None, shard: str = "auto"):
         light = self.propagate(E0)
+        self._last_light = light
         if events is not None:
             events[1].record()
             events[2].record()

@@ -69,11 +69,11 @@ def _worker(rank, world, port, out_dir):
         sel = items[(items >= lo) & (items < hi)] - lo
         score[r, sel] = float("-inf")
     v, ix = torch.topk(score, k)
-    cand_i = [torch.empty_like(ix) for _ in range(world)]
-    cand_v = [torch.empty_like(v) for _ in range(world)]
-    dist.all_gather(cand_i, ix + lo)
-    dist.all_gather(cand_v, v)
-    midx, mval = parallel.merge_candidates_reference(torch.stack(cand_i), torch.stack(cand_v), k)
+    # the product's exchange: ids and scores packed into ONE int32 collective (parallel.gather_packed)
+    all_i, all_v = parallel.gather_packed(ix + lo, v, world)
+    assert all_i.dtype == torch.int64 and all_v.dtype == torch.float32 and all_i.shape == (world,) + tuple(ix.shape)
+    assert torch.equal(all_i[rank], ix + lo) and torch.equal(all_v[rank], v)          # bit-exact round trip
+    midx, mval = parallel.merge_candidates_reference(all_i, all_v, k)
     s_full = (full[:nu].double() @ full[nu:].double().t()).numpy()
     for r, items in enumerate(ref.all_pos(users.numpy())):
         s_full[r, items] = -np.inf
@@ -102,6 +102,10 @@ def test_partition_and_merge_single_process():
     cv = torch.tensor([[[2.0, 1.0]], [[2.0, 0.5]]])
     idx, val = parallel.merge_candidates_reference(ci, cv, 3)
     assert idx.tolist() == [[5, 7, 1]] and val.tolist() == [[2.0, 2.0, 1.0]]
+    # packing keeps every bit of the scores (incl. -inf padding and the -1 "no item" id)
+    pi = torch.tensor([[3, -1, 2_000_000_000]]); pv = torch.tensor([[1.5, float("-inf"), -1024.0]])
+    ui, uv = parallel.unpack_candidates(parallel.pack_candidates(pi, pv))
+    assert torch.equal(ui, pi) and torch.equal(uv, pv)
 
 
 def test_upload_slices_tile_the_stacked_table():
