@@ -774,6 +774,9 @@ struct GqRescoreParams {
 };
 
 constexpr int RS_WARPS = 8;
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 4          // latency-bound (dependent global loads per row): 32 resident warps per SM
+#endif
 constexpr int RS_CAP = 160;      // candidate buffer per warp: compressed to the best K whenever > RS_CAP - 64 are held
 constexpr int RS_KMAX = 32;
 constexpr int RS_KTOT_MAX = 384;
@@ -902,7 +905,7 @@ __device__ __forceinline__ void rs_process(const GqRescoreParams& rp, const int3
   }
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32)
+__global__ void __launch_bounds__(RS_WARPS * 32, RS_MIN_BLOCKS)
 k_rescore_topk(const GqRescoreParams rp) {
   __shared__ __align__(16) __nv_bfloat16 s_user[RS_WARPS][RS_KTOT_MAX];
   __shared__ float s_bv[RS_WARPS][RS_CAP];

@@ -13,7 +13,7 @@ for r in rows[hdr + 1:]:
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(v[1] for v in agg.values())
 out.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-out.write(f"# command: python bench.py --steps 2 --warmup 1 --no-cpu   (3 warm-up + 2 timed + 3+2 e2e steps)\n")
+out.write(f"# command: python bench.py --steps 2 --warmup 1 --no-cpu --scale-leg off --min-seconds 0 --no-check   (3 warm-up + 2 timed + 3+2 e2e steps)\n")
 out.write(f"{'kernel':72s} {'launches':>8s} {'total_ms':>10s} {'avg_us':>10s} {'share':>7s}\n")
 for n, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
     out.write(f"{n:72s} {c:8d} {v / 1e6:10.3f} {v / c / 1e3:10.1f} {v / tot:7.3f}\n")
@@ -45,7 +45,7 @@ ir, iw, ik = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), 
 def to_bytes(v, unit):
     return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 sp = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:] if r[ik].startswith("void k_spmm") or r[ik].startswith("k_spmm_fixed")]
-sc = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:] if "k_score_topk_tc" in r[ik]]
+sc = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:] if "k_score_topk_tc" in r[ik] or "k_score_topk_gq" in r[ik]]
 key = os.environ.get("LGX_TRAFFIC_KEY", "amazon-book:bf16")
 path = "profiles/traffic.json"
 alltr = json.load(open(path)) if os.path.exists(path) else {}
