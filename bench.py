@@ -168,20 +168,11 @@ def cpu_baseline_sample(shape, u, i, ue, ie, budget_s=20.0):
             "propagate_ms": t_prop * 1e3, "edges_per_s": N_LAYERS * 2 * E / t_prop, "hoisted_users_per_s": hoisted}
 
 
-def check_timed_launch(step_fn, engine, E0, light, all_users, nu, mi, d, u, i, mode, g, _lgx, n_sample=512):
-    """Run the step once and check sampled users of ITS result: fp64 CPU scores from the same propagated embeddings,
-    train items masked, tests/-style 'identical up to ties' (tolerance 1e-2 bf16, 1e-5 bf16x3, 2e-6 fp32)."""
+def check_timed_launch(idx, emb, nu, mi, u, i, mode, n_sample=512):
+    """Check sampled users of the step's result: fp64 CPU scores from the same propagated embeddings, train items
+    masked, tests/-style 'identical up to ties' (tolerance 1e-2 bf16, 1e-5 bf16x3, 2e-6 fp32)."""
     import torch
     from oracle import lightgcn_oracle as O
-    if step_fn is not None:
-        idx, val = step_fn()
-        emb = light
-    else:
-        idx, val = engine.step(E0, all_users, K_TOP, _lgx.MODES[mode], shard="auto")
-        emb = engine.last_light() if hasattr(engine, "last_light") else None
-        if emb is None:
-            return {"ok": True, "skipped": "engine does not expose the gathered layer"}
-    torch.cuda.synchronize()
     tol = {"fp32": 2e-6, "bf16x3": 1e-5, "bf16": 1e-2}[mode]
     rng = np.random.default_rng(11)
     rows = np.sort(rng.choice(nu, size=min(n_sample, nu), replace=False))
@@ -276,7 +267,9 @@ def run_ours(args, shape):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a bounded collective timeout: a rank that dies must not hold the other GPUs for the default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
         dist.barrier()                        # ranks > 0 wait for rank 0's build check
     peaks = load_peaks()
     nu, mi, E, d = shape
@@ -365,10 +358,20 @@ def run_ours(args, shape):
     # ---- the launch that is about to be timed is checked first: sampled users against fp64 CPU scores of the same
     # propagated embeddings with the users' train items masked ("identical up to ties", tolerance per mode)
     parity = None
-    if rank == 0 and not huge and u is not None and not args.no_check:
-        parity = check_timed_launch(step_resident if engine is None else None, engine, E0, light, all_users, nu, mi, d, u, i, mode, g, _lgx)
-        if parity is not None and not parity["ok"]:
-            raise SystemExit(f"bench.py: the timed launch fails its parity check: {parity}")
+    if not huge and u is not None and not args.no_check:
+        # every rank runs the step (it contains collectives at N > 1); rank 0 checks its copy of the result
+        if engine is None:
+            chk_idx, chk_val = step_resident()
+            chk_emb = light
+        else:
+            chk_idx, chk_val = engine.step(E0, all_users, K_TOP, mode_id, shard=args.shard)
+            chk_emb = engine.last_light()
+        torch.cuda.synchronize()
+        if rank == 0:
+            parity = check_timed_launch(chk_idx, chk_emb, nu, mi, u, i, mode)
+            if not parity["ok"]:
+                print(f"bench.py: the timed launch fails its parity check: {parity}", file=sys.stderr, flush=True)
+        del chk_idx, chk_val
     barrier()
 
     for _ in range(max(args.warmup, 3)):

@@ -1028,9 +1028,14 @@ GqConfig gq_config(int d, int K, int mode) {
   return c;
 }
 
+// per-unit overhead of a (user tile, item split) unit in item tiles of 256, for the wave-aware split planner
+constexpr double kGqUnitOverheadTiles = 14.0;
 ScorePlan gq_plan(int B, int M, int sms) {
-  static const int forced = [] { const char* e = std::getenv("LGX_SCORE_SPLITS"); return e ? std::atoi(e) : 0; }();
-  static const double c0 = [] { const char* e = std::getenv("LGX_SCORE_UNIT_OVERHEAD"); return e ? std::atof(e) : 14.0; }();
+  // both knobs are re-read on every call (experiments sweep them inside one process)
+  const char* es = std::getenv("LGX_SCORE_SPLITS");
+  const char* eo = std::getenv("LGX_SCORE_UNIT_OVERHEAD");
+  const int forced = es ? std::atoi(es) : 0;
+  const double c0 = eo ? std::atof(eo) : kGqUnitOverheadTiles;
   ScorePlan p = plan_score_waves(B, M, GQ_TILE_U, GQ_TILE_I, sms, c0);
   if (forced > 0) {
     const int r = std::max(1, std::min(forced, std::min(p.n_item_tiles, kMaxSplits)));

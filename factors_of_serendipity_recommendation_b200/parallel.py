@@ -54,6 +54,61 @@ def shard_csr(indptr, indices, values, row_order, rank: int, world: int):
     return local_ptr, cols, vals, n_local, new_id, old_of_new
 
 
+def build_local_csr(n_users: int, m_items: int, users_part: torch.Tensor, items_part: torch.Tensor, rank: int, world: int,
+                    group=None):
+    """SHARDED graph build: every rank holds an arbitrary slice of the interaction list (an edge partition) and
+    ends up with ITS row block of D^-1/2 A D^-1/2 -- no rank ever holds the whole graph.  The reference's analogue is
+    the chunked assembly of TF/utility/load_data.py:113-118 (row folds of the normalised adjacency); the contract is
+    PT/dataloader.py:339-376.
+
+      1. degrees: local bincount of both endpoints + all-reduce (duplicate (u, i) pairs count twice, like scipy's
+         summing constructor, PT/dataloader.py:288);
+      2. row partition: the same degree-sorted cyclic deal as shard_csr (stable sort of the degree table, identical
+         on every rank), node ids relabelled to rank * n_local + local;
+      3. both directed copies of every edge go to the owner of their ROW (one all-to-all of 64-bit keys);
+      4. the owner sorts its keys by (local row, original column), merges duplicates into multiplicities and
+         forms value = fl(fl(dinv[row] * mult) * dinv[col]), dinv = correctly rounded fp32 of deg^-1/2.
+
+    Pure index arithmetic on torch tensors (CPU with gloo or CUDA with NCCL).  For interaction lists without
+    duplicate pairs the result equals shard_csr(canonical CSR) bit for bit (tests/test_parallel_cpu.py).
+    -> (indptr_local int64 [n_local+1], cols int32, vals f32, n_local, new_id, old_of_new, degree int64 [N])"""
+    dev = users_part.device
+    N = n_users + m_items
+    u = users_part.to(torch.int64)
+    it = items_part.to(torch.int64) + n_users
+    deg = torch.zeros(N, dtype=torch.int64, device=dev)
+    ones = torch.ones(u.numel(), dtype=torch.int64, device=dev)
+    deg.index_add_(0, u, ones)
+    deg.index_add_(0, it, ones)
+    if world > 1:
+        dist.all_reduce(deg, group=group)
+    order = torch.sort(deg, descending=True, stable=True).indices           # == the library's stable radix sort by row length
+    n_local, new_id, old_of_new = partition_rows(order, world)
+    rows = torch.cat([u, it])
+    cols = torch.cat([it, u])
+    owner = new_id[rows] // n_local
+    keys = rows * N + cols
+    if world > 1:
+        perm = torch.sort(owner, stable=True).indices
+        keys = keys[perm]
+        send = torch.bincount(owner, minlength=world)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        got = torch.empty(int(recv.sum()), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(got, keys, output_split_sizes=recv.tolist(), input_split_sizes=send.tolist(), group=group)
+        keys = got
+    r_old, c_old = keys // N, keys % N
+    local = new_id[r_old] - rank * n_local
+    skey, mult = torch.unique_consecutive(torch.sort(local * N + c_old).values, return_counts=True)
+    l_row, c_old = skey // N, skey % N
+    ptr = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(torch.bincount(l_row, minlength=n_local), 0)
+    dinv = torch.where(deg > 0, (1.0 / torch.sqrt(deg.to(torch.float64))).to(torch.float32), torch.zeros((), device=dev))
+    mine = old_of_new[rank * n_local:(rank + 1) * n_local]
+    vals = (dinv[mine[l_row]] * mult.to(torch.float32)) * dinv[c_old]
+    return ptr, new_id[c_old].to(torch.int32), vals, n_local, new_id, old_of_new, deg
+
+
 def item_shard_bounds(m_items: int, rank: int, world: int):
     per = (m_items + world - 1) // world
     lo = min(m_items, rank * per)
@@ -152,6 +207,41 @@ class ShardedEngine:
         self.X = [torch.zeros(n_tot, d, device=device) for _ in range(2)]       # gathered layers (ping-pong)
         self.Y = torch.empty(self.n_local, d, device=device)                    # my rows of the next layer
         self.full_mean = torch.empty(n_tot, d, device=device)
+
+    @classmethod
+    def from_edge_partition(cls, n_users: int, m_items: int, users_part, items_part, d: int, n_layers: int, rank: int,
+                            world: int, device, propagate: str = "fused"):
+        """Row-sharded propagation engine built WITHOUT the full graph on any rank (build_local_csr): for graphs beyond
+        one GPU.  Scoring with the train mask needs the users' rows of the full graph and is not wired to this
+        constructor (score(...) raises); propagate() works as in the other modes."""
+        from . import _lgx
+        self = cls.__new__(cls)
+        self._lgx = _lgx
+        self.g_full = None
+        self.n_users, self.m_items, self.d, self.L = n_users, m_items, d, n_layers
+        self.rank, self.world, self.dev = rank, world, device
+        self.lo, self.hi = item_shard_bounds(m_items, rank, world)
+        if propagate not in ("fused", "allgather"):
+            raise ValueError("from_edge_partition supports propagate='fused' or 'allgather'")
+        self.mode = propagate
+        self.peers = None
+        self._last_light = None
+        ptr, cols, vals, self.n_local, self.new_id, self.old_of_new, self.degree = build_local_csr(
+            n_users, m_items, users_part.to(device), items_part.to(device), rank, world)
+        self.local = _lgx.Graph.from_csr(ptr, cols, vals, n_cols=world * self.n_local, n_users=0, m_items=0)
+        del ptr, cols, vals
+        self.gather_src = self.old_of_new.clamp(min=0)
+        self.pad_mask = (self.old_of_new < 0)
+        self.has_pad = bool(self.pad_mask.any().item())
+        n_tot = world * self.n_local
+        self.S = torch.empty(self.n_local, d, device=device)
+        if self.mode == "fused":
+            self._setup_peers(n_tot, d)
+            return self
+        self.X = [torch.zeros(n_tot, d, device=device) for _ in range(2)]
+        self.Y = torch.empty(self.n_local, d, device=device)
+        self.full_mean = torch.empty(n_tot, d, device=device)
+        return self
 
     def _setup_peers(self, n_tot: int, d: int):
         """Gathered layers live in IPC-shared allocations; exchange the handles once."""
@@ -256,6 +346,9 @@ class ShardedEngine:
                        the split that scales when the catalogue fits one GPU (measured: DESIGN.md).
         shard="auto" : users when every rank still gets >= 1 tile of 128 users, else items."""
         _lgx = self._lgx
+        if self.g_full is None:
+            raise RuntimeError("this engine was built from an edge partition: the train mask of the full graph is not "
+                               "available on any rank (propagation only)")
         B = users.numel()
         if shard == "auto":
             shard = "users" if B >= self.world * 128 else "items"

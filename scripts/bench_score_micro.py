@@ -21,13 +21,24 @@ def run_variant(args):
     gen = torch.Generator(device="cuda").manual_seed(1)
     U = torch.empty(nu, d, device="cuda").normal_(std=0.1, generator=gen)
     I = torch.empty(mi, d, device="cuda").normal_(std=0.1, generator=gen)
-    users = torch.arange(nu, device="cuda")
+    if args.users:
+        nu_s = min(nu, args.users)
+        U = U[:nu_s].contiguous()
+    else:
+        nu_s = nu
+    users = torch.arange(nu_s, device="cuda")
     Uo = _lgx.pack_operand(U, None, mid, False)
     Io = _lgx.pack_operand(I, None, mid, True)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     out = {}
-    for dbg in args.dbg:
-        os.environ["LGX_GQ_DEBUG"] = str(dbg)
+    sweep = [("dbg", x) for x in args.dbg] if args.splits is None else [("splits", x) for x in args.splits]
+    for kind, dbg in sweep:
+        if kind == "dbg":
+            os.environ["LGX_GQ_DEBUG"] = str(dbg)
+        else:
+            os.environ["LGX_SCORE_SPLITS"] = str(dbg)
+            if dbg == 0:
+                os.environ.pop("LGX_SCORE_SPLITS")
         for _ in range(3):
             _lgx.score_topk(g, Uo, users, Io, d, args.k, mid)
         ts = []
@@ -36,8 +47,9 @@ def run_variant(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); _lgx.score_topk(g, Uo, users, Io, d, args.k, mid); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        out[f"dbg{dbg}"] = round(statistics.median(ts), 4)
-    print(json.dumps({"variant": args.name, "d": d, "mode": args.mode, "nomask": args.nomask, "ms": out}), flush=True)
+        out[f"{kind}{dbg}"] = round(statistics.median(ts), 4)
+    plan = _lgx.score_plan(nu_s, mi, d, args.k, mid)
+    print(json.dumps({"variant": args.name, "d": d, "mode": args.mode, "nomask": args.nomask, "users": nu_s, "planner": plan, "ms": out}), flush=True)
 
 
 def main():
@@ -49,6 +61,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--nomask", action="store_true")
     ap.add_argument("--dbg", type=int, nargs="*", default=[0])
+    ap.add_argument("--users", type=int, default=0, help="score only the first N users (0 = all)")
+    ap.add_argument("--splits", type=int, nargs="*", default=None, help="sweep LGX_SCORE_SPLITS over these values (0 = planner)")
     ap.add_argument("--name", default="default")
     ap.add_argument("--variants", nargs="*", default=None, help="name=ENV:VAL,ENV:VAL ... each run in a child process")
     args = ap.parse_args()
@@ -61,7 +75,9 @@ def main():
             k, _, val = kv.partition(":")
             env[k] = val
         cmd = [sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--d", str(args.d), "--k", str(args.k),
-               "--mode", args.mode, "--iters", str(args.iters), "--name", name, "--dbg", *map(str, args.dbg)]
+               "--mode", args.mode, "--iters", str(args.iters), "--name", name, "--users", str(args.users), "--dbg", *map(str, args.dbg)]
+        if args.splits is not None:
+            cmd += ["--splits", *map(str, args.splits)]
         if args.nomask:
             cmd.append("--nomask")
         subprocess.run(cmd, env=env, check=False, timeout=600)

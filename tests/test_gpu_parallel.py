@@ -41,6 +41,15 @@ def _worker(rank, world, port, out_dir):
                 assert (light - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (mode, rep)
             if mode != "allgather":
                 eng.close()
+        # sharded graph build: every rank starts from its slice of the interaction list, never sees the full graph
+        ut, it_ = torch.from_numpy(u), torch.from_numpy(i)
+        for mode in ("fused", "allgather"):
+            eng2 = parallel.ShardedEngine.from_edge_partition(nu, mi, ut[rank::world], it_[rank::world], d, L, rank, world,
+                                                              dev, propagate=mode)
+            for rep in range(2):
+                light = eng2.propagate(E0)
+                assert (light - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), ("edge partition", mode, rep)
+            eng2.close()
         for mode in ("fp32", "bf16x3"):
             idx1, val1 = m.topk(users, k, mode=mode)
             for shard in ("items", "users"):

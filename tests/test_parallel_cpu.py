@@ -41,6 +41,15 @@ def _worker(rank, world, port, out_dir):
     assert sum(int(x) for x in nnz_all) == indices.numel()
     assert max(int(x) for x in nnz_all) <= 1.15 * indices.numel() / world       # degree-cyclic deal balances nnz
 
+    # SHARDED BUILD (no rank holds the whole graph): every rank starts from an arbitrary half of the interaction list and
+    # must end up with exactly the row block shard_csr cuts out of the canonical CSR -- bit for bit
+    sel = torch.from_numpy(np.random.default_rng(9).permutation(len(u)))[rank::world]
+    ptr2, cols2, vals2, n_local2, new_id2, old2, deg2 = parallel.build_local_csr(
+        nu, mi, torch.from_numpy(u)[sel], torch.from_numpy(i)[sel], rank, world)
+    assert n_local2 == n_local and torch.equal(new_id2, new_id) and torch.equal(old2, old_of_new)
+    assert torch.equal(deg2, torch.from_numpy(ref.degree).long())
+    assert torch.equal(ptr2, ptr) and torch.equal(cols2, cols) and torch.equal(vals2, vals)
+
     A_local = torch.sparse_csr_tensor(ptr, cols.long(), vals, (n_local, world * n_local))
     E0 = torch.cat([ue, ie])
     X = torch.zeros(world * n_local, d)
@@ -102,6 +111,20 @@ def test_partition_and_merge_single_process():
     cv = torch.tensor([[[2.0, 1.0]], [[2.0, 0.5]]])
     idx, val = parallel.merge_candidates_reference(ci, cv, 3)
     assert idx.tolist() == [[5, 7, 1]] and val.tolist() == [[2.0, 2.0, 1.0]]
+    # sharded build at world 1 == the oracle's canonical CSR, duplicates merged into multiplicities (value 2)
+    from oracle import lightgcn_oracle as O
+    uu = np.array([0, 0, 1, 2, 2, 2, 3], dtype=np.int32)
+    ii = np.array([1, 1, 0, 2, 0, 1, 2], dtype=np.int32)      # (0, 1) appears twice
+    indptr, indices, data, degree = O.build_norm_adj(4, 3, uu, ii)
+    ptr, cols, vals, n_local, new_id, old, deg = parallel.build_local_csr(4, 3, torch.from_numpy(uu), torch.from_numpy(ii), 0, 1)
+    order = torch.from_numpy(O.degree_sorted_row_order(degree, indptr))
+    # world 1: local row l is global row old[l]; columns come back relabelled through new_id
+    assert torch.equal(deg, torch.from_numpy(degree).long())
+    for l in range(n_local):
+        g_row = int(old[l])
+        a, b = int(ptr[l]), int(ptr[l + 1])
+        assert old[cols[a:b].long()].tolist() == indices[indptr[g_row]:indptr[g_row + 1]].tolist()
+        assert np.array_equal(vals[a:b].numpy(), data[indptr[g_row]:indptr[g_row + 1]])
     # packing keeps every bit of the scores (incl. -inf padding and the -1 "no item" id)
     pi = torch.tensor([[3, -1, 2_000_000_000]]); pv = torch.tensor([[1.5, float("-inf"), -1024.0]])
     ui, uv = parallel.unpack_candidates(parallel.pack_candidates(pi, pv))
