@@ -27,7 +27,8 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
     aver_loss = torch.zeros((), device=dev)
     # config['cuda_graph']: after 3 eager steps (lazy initialisation happens there) the full-size batches
     # replay one captured graph of the whole step; the last, shorter batch runs eagerly
-    use_graph = bool(world.config.get("cuda_graph", False)) and getattr(bpr, "fused", False) and dev.type == "cuda"
+    use_graph = (bool(world.config.get("cuda_graph", False)) and getattr(bpr, "fused", False) and dev.type == "cuda"
+                 and not (getattr(Recmodel, "config", {}).get("dropout") and Recmodel.training))
     graphed = getattr(bpr, "_graphed", None)
     for batch_i, (bu, bp, bn) in enumerate(utils.minibatch(users, posItems, negItems, batch_size=bs)):
         if use_graph and len(bu) == bs and (graphed is not None or batch_i >= 3):

@@ -38,6 +38,7 @@ _SIGS = {
     "lgx_peer_close": (C.c_int, [_P]),
     "lgx_peer_copy": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_size_t, C.c_size_t, _P]),
     "lgx_peer_free": (C.c_int, [_P]),
+    "lgx_peer_barrier": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_uint32, _P]),
     "lgx_propagate_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "lgx_propagate_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "lgx_propagate_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
@@ -46,6 +47,8 @@ _SIGS = {
     "lgx_propagate_fwd_dropout": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, _P]),
     "lgx_propagate_bwd_dropout": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, _P]),
     "lgx_score_dense": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "lgx_score_minmax": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "lgx_score_bucket": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
     "lgx_pack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "lgx_pack_operand": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lgx_score_topk_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
@@ -299,6 +302,13 @@ class PeerBuffer:
             self.ptr = 0
 
 
+def peer_barrier(flag_ptrs, self_rank: int, epoch: int, device):
+    """Device-side cross-rank barrier over peer-mapped flag arrays (lgx_peer_barrier) on the current stream."""
+    arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+    with torch.cuda.device(device):
+        check(lib().lgx_peer_barrier(arr, len(flag_ptrs), self_rank, epoch & 0xFFFFFFFF or 1, stream()))
+
+
 def peer_copy(peer_ptrs, self_rank: int, offset_bytes: int, nbytes: int, cuda_stream, device):
     """P2P DMA of one byte range of my buffer into every other rank's buffer (one async copy per peer)."""
     arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
@@ -321,6 +331,28 @@ def score_dense(U, users, I, apply_sigmoid=True, out=None):
         out = torch.empty(B, M, dtype=torch.float32, device=I.device)
     with torch.cuda.device(I.device):
         check(lib().lgx_score_dense(ptr(U), ptr(users), B, ptr(I), M, d, ptr(out), int(apply_sigmoid), stream()))
+    return out
+
+
+def score_minmax(U, I):
+    """(min, max) of fp16(U I^T) as a device float[2] tensor -- recommend.py:377 without the [n_user, n_item] matrix."""
+    require_cuda(U, I)
+    out = torch.empty(2, dtype=torch.float32, device=I.device)
+    ws = torch.empty(2, dtype=torch.int32, device=I.device)
+    with torch.cuda.device(I.device):
+        check(lib().lgx_score_minmax(ptr(U), U.shape[0], ptr(I), I.shape[0], I.shape[1], ptr(out), ptr(ws), stream()))
+    return out
+
+
+def score_bucket(U, users, I, min_dis: float, inter: float, out=None):
+    """int8 labels [B, M] = floor((fp16(score) - min_dis) / inter) in fp16 arithmetic (recommend.py:380)."""
+    require_cuda(U, users, I, out)
+    B = U.shape[0] if users is None else users.numel()
+    M, d = I.shape
+    if out is None:
+        out = torch.empty(B, M, dtype=torch.int8, device=I.device)
+    with torch.cuda.device(I.device):
+        check(lib().lgx_score_bucket(ptr(U), ptr(users), B, ptr(I), M, d, float(min_dis), float(inter), ptr(out), stream()))
     return out
 
 

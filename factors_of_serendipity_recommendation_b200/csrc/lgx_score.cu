@@ -4,6 +4,7 @@
 // Replaces PT/model.py:181-183 (index_select + cuBLAS SGEMM + sigmoid), PT/Procedure.py:129-134
 // (index_put_ of -1024 over train items) and :135 (torch.topk).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -92,6 +93,73 @@ k_score_dense(const float* __restrict__ U, const int64_t* __restrict__ users, in
       float s = acc.c[i][j];
       if (apply_sigmoid) s = 1.0f / (1.0f + expf(-s));   // nn.Sigmoid, PT/model.py:183
       out[(int64_t)u * M + it] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The candidate-bucketing primitive of the serendipity pipeline (/root/reference/recommend.py:375-380):
+//     mat_dis = np.dot(emb_user, emb_item.T).astype(np.float16); max_dis, min_dis = mat_dis.max() + eps, mat_dis.min()
+//     mat_label = np.floor((mat_dis - min_dis) / ((max_dis - min_dis) / num_fold)).astype(np.int8)
+// The reference materialises the [n_user, n_item] fp16 matrix on the host; here pass 1 reduces min / max of the
+// fp16-rounded scores on the fly and pass 2 writes the int8 labels of a user batch, in the same fp16 arithmetic
+// (subtract and divide rounded to half, like numpy's float16 ufuncs).
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(256)
+k_score_minmax(const float* __restrict__ U, int B, const float* __restrict__ I, int M, int d, unsigned* __restrict__ mm) {
+  __shared__ __align__(16) float Us[TK][TU + 4];
+  __shared__ __align__(16) float Is[TK][TI + 4];
+  __shared__ unsigned s_min, s_max;
+  if (threadIdx.x == 0) { s_min = 0xffffffffu; s_max = 0u; }
+  const int j0 = blockIdx.x * TI, u0 = blockIdx.y * TU;
+  TileAcc acc;
+  sgemm_tile(U, nullptr, B, I, M, d, u0, j0, Us, Is, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  unsigned lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (u0 + ty * 4 + i < B && j0 + tx * 4 + j < M) {
+        const unsigned o = f32_ordered(__half2float(__float2half_rn(acc.c[i][j])));
+        lo = min(lo, o);
+        hi = max(hi, o);
+      }
+  __syncthreads();
+  atomicMin(&s_min, lo);
+  atomicMax(&s_max, hi);
+  __syncthreads();
+  if (threadIdx.x == 0) { atomicMin(mm, s_min); atomicMax(mm + 1, s_max); }
+}
+__global__ void k_minmax_decode(const unsigned* __restrict__ mm, float* __restrict__ out2) {
+  for (int k = 0; k < 2; ++k) {
+    const unsigned u = mm[k];
+    out2[k] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_score_bucket(const float* __restrict__ U, const int64_t* __restrict__ users, int B, const float* __restrict__ I, int M,
+               int d, float min_dis, float inter, int8_t* __restrict__ labels) {
+  __shared__ __align__(16) float Us[TK][TU + 4];
+  __shared__ __align__(16) float Is[TK][TI + 4];
+  const int j0 = blockIdx.x * TI, u0 = blockIdx.y * TU;
+  TileAcc acc;
+  sgemm_tile(U, users, B, I, M, d, u0, j0, Us, Is, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const __half hmin = __float2half_rn(min_dis), hint = __float2half_rn(inter);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int u = u0 + ty * 4 + i;
+    if (u >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = j0 + tx * 4 + j;
+      if (it >= M) continue;
+      const __half q = __hdiv(__hsub(__float2half_rn(acc.c[i][j]), hmin), hint);
+      labels[(int64_t)u * M + it] = (int8_t)(int)floorf(__half2float(q));
     }
   }
 }
@@ -293,6 +361,36 @@ int lgx_score_dense(const float* U, const int64_t* users, int32_t B, const float
   dim3 grid((M + TI - 1) / TI, (B + TU - 1) / TU);
   LGX_REQUIRE(grid.y <= 65535, "batch too large for one call (max 65535*64 users)");
   k_score_dense<<<grid, 256, 0, (cudaStream_t)stream>>>(U, users, B, I, M, d, out, apply_sigmoid);
+  LGX_CHECK_LAUNCH();
+  return LGX_OK;
+}
+
+int lgx_score_minmax(const float* U, int32_t B, const float* I, int32_t M, int32_t d, float* out2, void* workspace8,
+                     lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(U && I && out2 && workspace8, "NULL argument");
+  LGX_REQUIRE(B > 0 && M > 0 && d > 0, "B, M, d must be positive");
+  dim3 grid((M + TI - 1) / TI, (B + TU - 1) / TU);
+  LGX_REQUIRE(grid.y <= 65535, "batch too large for one call (max 65535*64 users)");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* mm = reinterpret_cast<unsigned*>(workspace8);
+  const unsigned init[2] = {0xffffffffu, 0u};
+  LGX_CHECK_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  k_score_minmax<<<grid, 256, 0, st>>>(U, B, I, M, d, mm);
+  k_minmax_decode<<<1, 1, 0, st>>>(mm, out2);
+  LGX_CHECK_LAUNCH();
+  return LGX_OK;
+}
+
+int lgx_score_bucket(const float* U, const int64_t* users, int32_t B, const float* I, int32_t M, int32_t d, float min_dis,
+                     float inter, int8_t* labels, lgx_stream stream) {
+  LGX_CHECK_DEVICE();
+  LGX_REQUIRE(U && I && labels, "NULL argument");
+  LGX_REQUIRE(B > 0 && M > 0 && d > 0, "B, M, d must be positive");
+  LGX_REQUIRE(inter > 0.0f, "inter must be positive");
+  dim3 grid((M + TI - 1) / TI, (B + TU - 1) / TU);
+  LGX_REQUIRE(grid.y <= 65535, "batch too large for one call (max 65535*64 users)");
+  k_score_bucket<<<grid, 256, 0, (cudaStream_t)stream>>>(U, users, B, I, M, d, min_dis, inter, labels);
   LGX_CHECK_LAUNCH();
   return LGX_OK;
 }

@@ -26,6 +26,12 @@ k_bpr_forward(const float* __restrict__ light, const float* __restrict__ E0, con
               float* __restrict__ per) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
+  // lgx_sample_bpr marks a triple it could not draw (a user without positives in per-user mode, a user who interacted
+  // with every item) with -1: such a triple contributes nothing (it used to index the last user's row as an item)
+  if (users[b] < 0 || users[b] >= n_users || pos[b] < 0 || neg[b] < 0) {
+    if (lane == 0) { per[b] = 0.f; per[B + b] = 0.f; per[2 * B + b] = 0.f; }
+    return;
+  }
   const int64_t ur = users[b], pr = (int64_t)n_users + pos[b], nr = (int64_t)n_users + neg[b];
   float sp = 0.f, sn = 0.f, reg = 0.f;
   for (int c = lane; c < d; c += 32) {
@@ -69,6 +75,7 @@ k_bpr_backward_light(const float* __restrict__ light, const int64_t* __restrict_
                      float grad_scale, const float* __restrict__ grad_scale_dev, float* __restrict__ G) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
+  if (users[b] < 0 || users[b] >= n_users || pos[b] < 0 || neg[b] < 0) return;      // undrawn triple (see k_bpr_forward)
   const int64_t ur = users[b], pr = (int64_t)n_users + pos[b], nr = (int64_t)n_users + neg[b];
   const float s = coef[b] * grad_scale * (grad_scale_dev ? __ldg(grad_scale_dev) : 1.0f);
   for (int c = lane; c < d; c += 32) {
@@ -86,6 +93,7 @@ k_bpr_backward_reg(const float* __restrict__ E0, const int64_t* __restrict__ use
                    const float* __restrict__ scale_dev, float* __restrict__ dE0) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
+  if (users[b] < 0 || users[b] >= n_users || pos[b] < 0 || neg[b] < 0) return;      // undrawn triple (see k_bpr_forward)
   if (scale_dev) scale *= __ldg(scale_dev);
   const int64_t rows[3] = {users[b], (int64_t)n_users + pos[b], (int64_t)n_users + neg[b]};
 #pragma unroll

@@ -262,10 +262,27 @@ class ShardedEngine:
         self.X[0].zero_()
         self.X[1].zero_()
         self._barrier_buf = torch.zeros(1, device=self.dev)
+        # device-side layer barrier: one peer-visible flag array per rank (LGX_BARRIER=nccl keeps the all-reduce)
+        import os
+        self._flag_barrier = os.environ.get("LGX_BARRIER", "flags") != "nccl"
+        self._epoch = 0
+        if self._flag_barrier:
+            self.pbuf["flags"] = _lgx.PeerBuffer((64,), self.dev)          # 64 x 4 bytes, used as uint32 slots
+            self.pbuf["flags"].tensor.zero_()
+            torch.cuda.synchronize(self.dev)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, self.pbuf["flags"].handle)
+            self.peers["flags"] = [self.pbuf["flags"].ptr if r == self.rank else self.pbuf["flags"].open_peer(everyone[r])
+                                   for r in range(self.world)]
         dist.barrier()
 
     def _layer_barrier(self):
-        dist.all_reduce(self._barrier_buf)        # stream-ordered: every rank's layer kernel has retired
+        """every rank's layer kernel has retired and its peer stores are visible (stream-ordered on every rank)"""
+        if self._flag_barrier:
+            self._epoch += 1
+            self._lgx.peer_barrier(self.peers["flags"], self.rank, self._epoch, self.dev)
+        else:
+            dist.all_reduce(self._barrier_buf)
 
     def close(self):
         if self.peers is not None:

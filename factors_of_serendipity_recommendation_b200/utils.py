@@ -22,11 +22,11 @@ class BPRLoss:
         self.model = recmodel
         self.weight_decay = config["decay"]
         self.lr = config["lr"]
-        self.fused = bool(config.get("fused_adam", False)) and getattr(recmodel, "_flat_if_fused", None) is not None
+        # the fused Adam needs the model's single [N, d] parameter buffer on a CUDA device (LightGCN after .cuda());
+        # any other model (PureMF, a model still on the host) keeps torch.optim.Adam like the reference
+        flat = recmodel._flat_if_fused() if getattr(recmodel, "_flat_if_fused", None) is not None else None
+        self.fused = bool(config.get("fused_adam", False)) and flat is not None and flat.is_cuda
         if self.fused:
-            flat = recmodel._flat_if_fused()
-            if flat is None:
-                raise RuntimeError("fused_adam needs the fused [N, d] parameter buffer (move the model to CUDA first)")
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat)
             self._state = torch.zeros(4, dtype=torch.int32, device=flat.device)   # device-side Adam step counter
@@ -44,8 +44,12 @@ class BPRLoss:
             loss.backward()
             flat = self.model._flat_if_fused()
             gu, gi = wu.grad, wi.grad
-            # the fused backward returns both gradients as views of one [N, d] buffer
-            if gu.data_ptr() + gu.numel() * 4 == gi.data_ptr():
+            # the fused backward returns both gradients as views of ONE [N, d] buffer: same storage, adjacent, and the
+            # storage really covers both (two separately allocated blocks can be adjacent by accident)
+            st_u, st_i = gu.untyped_storage(), gi.untyped_storage()
+            if (gu.is_contiguous() and gi.is_contiguous() and st_u.data_ptr() == st_i.data_ptr()
+                    and gu.data_ptr() + gu.numel() * 4 == gi.data_ptr()
+                    and gu.data_ptr() - st_u.data_ptr() + flat.numel() * 4 <= st_u.nbytes()):
                 grad = torch.as_strided(gu, (flat.shape[0], flat.shape[1]), (flat.shape[1], 1))
             else:
                 grad = torch.cat([gu, gi])
@@ -84,6 +88,10 @@ class GraphedStageOne:
         self.p.copy_(pos)
         self.n.copy_(neg)
         self.graph.replay()
+        # the replayed Adam kernel writes the parameter buffer through a raw pointer (no autograd version bump): drop the
+        # model's cached propagation / packed operands here, or computer() / topk() after graph steps would be stale
+        self.bpr.model._eval_cache = None
+        self.bpr.model._packed = {}
         return self.loss
 
 
@@ -237,3 +245,35 @@ def getLabel(test_data, pred_data):
     for i, truth in enumerate(test_data):
         out[i] = np.isin(np.asarray(pred_data[i]), np.asarray(truth))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+def export_embeddings(model, dataset_name: str | None = None, out_dir: str = "."):
+    """PT/main.py:31-41 (the --load branch): write the two RAW embedding tables as emb_user_<dataset>.npy /
+    emb_item_<dataset>.npy, the files the serendipity pipeline reads back (recommend.py:363-364).
+    -> (path_user, path_item)"""
+    import os
+    name = dataset_name if dataset_name is not None else world.dataset
+    pu = os.path.join(out_dir, f"emb_user_{name}.npy")
+    pi = os.path.join(out_dir, f"emb_item_{name}.npy")
+    np.save(pu, model.embedding_user.weight.detach().cpu().numpy())
+    np.save(pi, model.embedding_item.weight.detach().cpu().numpy())
+    return pu, pi
+
+
+def candidate_buckets(emb_user, emb_item, num_fold: int = 10, epsilon: float = 1e-8, user_batch: int = 8192, device="cuda"):
+    """recommend.py:375-380 on the GPU: yields (first_user, labels int8 [b, n_item]) per user batch plus the
+    (min_dis, max_dis, inter) triple, without ever holding the [n_user, n_item] matrix.
+    -> (min_dis, max_dis, inter, generator of (start, labels))"""
+    from . import _lgx
+    U = torch.as_tensor(np.asarray(emb_user), dtype=torch.float32).to(device).contiguous()
+    I = torch.as_tensor(np.asarray(emb_item), dtype=torch.float32).to(device).contiguous()
+    mm = _lgx.score_minmax(U, I).cpu().numpy().astype(np.float16)
+    min_dis = mm[0]
+    max_dis = mm[1] + epsilon                     # np.float16 + python float, as the reference writes it
+    inter = (max_dis - min_dis) / num_fold
+
+    def batches():
+        for s in range(0, U.shape[0], user_batch):
+            yield s, _lgx.score_bucket(U[s:s + user_batch].contiguous(), None, I, float(np.float16(min_dis)), float(np.float16(inter)))
+    return min_dis, max_dis, inter, batches()

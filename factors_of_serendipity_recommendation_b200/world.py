@@ -25,8 +25,10 @@ config = {
     "bigdata": False,
     # engine-only keys (absent from the reference)
     "score_mode": "bf16x3",       # fp32 | bf16 | bf16x3 for the fused top-K
-    "fused_adam": False,          # BPRLoss uses lgx_adam_step_dev instead of torch.optim.Adam
-    "cuda_graph": False,          # BPR_train_original replays one CUDA graph per full batch (needs fused_adam)
+    "fused_adam": True,           # BPRLoss uses lgx_adam_step_dev (one fused pass, device-side step counter) instead of
+                                  # torch.optim.Adam; parity-tested against the reference's first step
+    "cuda_graph": True,           # BPR_train_original replays one CUDA graph per full batch (needs fused_adam; off
+                                  # automatically with edge dropout, whose seed is a host value per call)
 }
 GPU = torch.cuda.is_available()
 device = torch.device("cuda" if GPU else "cpu")

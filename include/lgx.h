@@ -116,6 +116,12 @@ int lgx_peer_close(void* ptr);
 int lgx_peer_copy(void* const* peers_host, int32_t n_peers, int32_t self, size_t offset_bytes, size_t bytes,
                   lgx_stream stream);
 int lgx_peer_free(void* ptr);
+/* Cross-rank barrier between two layers of the fused exchange, on the device: every rank owns a peer-visible array of
+ * n_peers uint32 flags (lgx_peer_alloc, zero-initialised); the kernel writes `epoch` (> 0, growing by one per call on
+ * all ranks) into slot [self] of every rank's array and waits until its own array has reached `epoch`.  Stream-
+ * ordered after the layer's SpMM; a rank that never arrives makes the others trap after ~10 s instead of hanging. */
+int lgx_peer_barrier(void* const* flag_peers_host, int32_t n_peers, int32_t self, uint32_t epoch,
+                     lgx_stream stream);
 
 /* LightGCN.computer() (PT/model.py:145-177): out = mean(E0, A E0, ..., A^L E0), E0 = cat(users, items).
  * workspace: lgx_propagate_workspace_bytes(g, d, L) (two [n,d] ping-pong layers + spmm workspace).
@@ -150,6 +156,18 @@ int lgx_propagate_bwd_dropout(const lgx_graph* g, const float* g_scaled, float* 
  * apply_sigmoid; fp32 CUDA-core arithmetic like the reference's SGEMM.  users may be NULL (rows 0..B-1). */
 int lgx_score_dense(const float* U, const int64_t* users, int32_t B, const float* I, int32_t M,
                     int32_t d, float* out, int32_t apply_sigmoid, lgx_stream stream);
+
+/* Candidate bucketing of the serendipity pipeline (/root/reference/recommend.py:375-380, the same min / max scan over
+ * item-item products at /root/reference/utils.py:496-519): scores are the fp32 dot products rounded to fp16 like the
+ * reference's .astype(np.float16).
+ *   lgx_score_minmax : out2 (device float[2]) = {min, max} of fp16(<U[b], I[j]>) over all b < B, j < M; the [B, M] matrix
+ *                      is never materialised.  workspace8: 8 bytes of device scratch.
+ *   lgx_score_bucket : labels[b, j] = int8(floor(fp16(fp16(score - min_dis) / inter))) for a user batch (users may be
+ *                      NULL = rows 0..B-1 of U); min_dis and inter are rounded to fp16 like numpy's float16 ufuncs do. */
+int lgx_score_minmax(const float* U, int32_t B, const float* I, int32_t M, int32_t d, float* out2,
+                     void* workspace8, lgx_stream stream);
+int lgx_score_bucket(const float* U, const int64_t* users, int32_t B, const float* I, int32_t M, int32_t d,
+                     float min_dis, float inter, int8_t* labels, lgx_stream stream);
 
 /* Pack fp32 rows into the bf16 operand layout the tcgen05 kernel reads: [rows, K] bf16 with
  * K = d (LGX_SCORE_BF16) or 3d (LGX_SCORE_BF16X3; is_items picks [hi|lo|hi] vs users' [hi|hi|lo]).

@@ -107,3 +107,38 @@ def test_synth10m_layer_sampled_rows():
         ref = (values[lo:hi].astype(np.float64)[:, None] * Xc[indices[lo:hi]]).sum(0)
         scale = np.abs(values[lo:hi].astype(np.float64)[:, None] * Xc[indices[lo:hi]]).sum(0).max() + 1e-30
         assert np.abs(Yc[r] - ref).max() <= 1e-5 * scale, r
+
+
+def test_yelp2018_shape_stage_one_vs_oracle():
+    """configs[1] shape (31 668 users / 38 048 items / 1.56 M edges, d = 64, 3 layers): one BPRLoss.stageOne step
+    (fused bpr_loss forward + backward through the propagation + Adam) against the oracle's torch step on the CPU."""
+    from factors_of_serendipity_recommendation_b200 import dataloader, model, synth, utils, world
+    nu, mi, E, d = synth.SHAPES["yelp2018"]
+    u, i = synth.make_interactions(nu, mi, E, seed=2020)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=2020)
+    cfg = dict(world.config)
+    cfg.update(lightGCN_n_layers=3, latent_dim_rec=d, pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy(), lr=0.001,
+               decay=1e-4, fused_adam=True)
+    ds = dataloader.InteractionDataset(nu, mi, u, i, device="cuda")
+    m = model.LightGCN(cfg, ds).cuda().train()
+    S = ds.getGraphHandle().sample_bpr(2048, per_user=0, seed=7).cpu()
+    bu, bp, bn = S[:, 0].contiguous(), S[:, 1].contiguous(), S[:, 2].contiguous()
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=3, user_emb=ue, item_emb=ie)
+    opt = torch.optim.Adam([ref.user_w, ref.item_w], lr=cfg["lr"])
+    rl, rr = ref.bpr_loss(bu, bp, bn)
+    want = O.stage_one(ref, opt, bu, bp, bn, cfg["decay"])
+    loss, reg = m.bpr_loss(bu.cuda(), bp.cuda(), bn.cuda())
+    assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
+    assert abs(reg.item() - rr.item()) <= 1e-5 * abs(rr.item())
+    bpr = utils.BPRLoss(m, cfg)
+    assert bpr.fused
+    got = bpr.stageOne(bu.cuda(), bp.cuda(), bn.cuda())
+    assert abs(got - want) <= 1e-5 * abs(want)
+    du = m.embedding_user.weight.detach().cpu() - ue
+    di = m.embedding_item.weight.detach().cpu() - ie
+    ru, ri = ref.user_w.detach() - ue, ref.item_w.detach() - ie
+    # Adam's first step is ~ lr * sign(g): compare the update itself, 1 % of lr (fp32 atomics reorder the row sums)
+    assert (du - ru).abs().max().item() <= 1e-2 * cfg["lr"]
+    assert (di - ri).abs().max().item() <= 1e-2 * cfg["lr"]
+    touched = (ru.abs().sum(1) > 0).float().mean().item()
+    assert touched > 0.05                                   # the step reaches far beyond the 2048 sampled users

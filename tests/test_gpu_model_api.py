@@ -144,3 +144,34 @@ def test_foreign_reference_style_dataset_drives_lightgcn():
     rl, rr = ref.bpr_loss(bu, bp, bn)
     assert abs(loss.item() - rl.item()) <= 1e-5 * max(1.0, abs(rl.item()))
     assert abs(reg.item() - rr.item()) <= 1e-5 * max(1.0, abs(rr.item()))
+
+
+def test_embedding_export_and_candidate_buckets(tmp_path):
+    """PT/main.py:31-41 (.npy export of the raw tables) and the min / max / 10-bucket labelling of
+    /root/reference/recommend.py:375-380, checked against the reference's numpy expressions on the same tables."""
+    from factors_of_serendipity_recommendation_b200 import dataloader, model, utils, world
+    nu, mi, u, i, ue, ie, _ = _problem(seed=8, nu=301, mi=517, E=8000)
+    cfg = dict(world.config)
+    cfg.update(lightGCN_n_layers=2, latent_dim_rec=64, pretrain=1, user_emb=ue.numpy(), item_emb=ie.numpy())
+    ds = dataloader.InteractionDataset(nu, mi, u, i, device="cuda")
+    m = model.LightGCN(cfg, ds).cuda().eval()
+    pu, pi = utils.export_embeddings(m, "unit", out_dir=str(tmp_path))
+    emb_user, emb_item = np.load(pu), np.load(pi)
+    assert pu.endswith("emb_user_unit.npy") and pi.endswith("emb_item_unit.npy")
+    assert np.array_equal(emb_user, ue.numpy()) and np.array_equal(emb_item, ie.numpy())
+    # the reference, verbatim (recommend.py:375-380)
+    num_fold, epsilon = 10, 1e-8
+    mat_dis = np.dot(emb_user, emb_item.T).astype(np.float16)
+    max_dis, min_dis = np.max(mat_dis) + epsilon, np.min(mat_dis)
+    inter = (max_dis - min_dis) / num_fold
+    mat_label = np.floor((mat_dis - min_dis) / inter).astype(np.int8)
+    got_min, got_max, got_inter, batches = utils.candidate_buckets(emb_user, emb_item, num_fold, epsilon, user_batch=128)
+    assert np.float16(got_min) == np.float16(min_dis) and np.float16(got_max) == np.float16(max_dis)
+    assert np.float16(got_inter) == np.float16(inter)
+    labels = np.concatenate([lab.cpu().numpy() for _, lab in batches])
+    assert labels.shape == mat_label.shape and labels.dtype == np.int8
+    diff = labels.astype(np.int32) - mat_label.astype(np.int32)
+    # the fp32 dot products are summed in a different order than numpy's BLAS: a score that sits on an fp16 rounding
+    # boundary may land in the neighbouring bucket
+    assert np.abs(diff).max() <= 1 and (diff != 0).mean() < 2e-3
+    assert labels.min() >= 0 and labels.max() <= num_fold
