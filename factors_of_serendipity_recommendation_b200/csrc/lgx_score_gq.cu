@@ -1003,26 +1003,37 @@ GqConfig gq_config(int d, int K, int mode) {
   c.k_blocks = ktot / GQ_KBLK;
   static const int forced_q = [] { const char* e = std::getenv("LGX_SCORE_QCAP"); return e ? std::atoi(e) : 0; }();
   static const int union_env = [] { const char* e = std::getenv("LGX_SCORE_UNION"); return e ? std::atoi(e) : 1; }();
-  // queue depth vs B-ring depth, first fit: 32-row queues with >= 3 ring stages, else 24 / 16 / 8 rows with >= 2
+  // Queue depth vs B-ring depth.  The ring matters more: with fewer than 3 stages in flight the TMA latency shows
+  // (bf16x3 d = 64, three K blocks per tile: 2.21 ms with 24-row queues + 2 stages, 1.95 ms with 8-row queues + 3
+  // stages), so take the deepest queue that still leaves 3 stages, else the configuration with the most stages.
   const int cands[4] = {32, 24, 16, 8};
   bool found = false;
-  for (int i = 0; i < 4 && !found; ++i) {
-    const int qc = cands[i];
-    if (forced_q && qc != forced_q) continue;
-    size_t fx = 1024 + (size_t)c.k_blocks * GQ_A_BLOCK + GQ_A_BLOCK + GQ_STAGE + (size_t)qc * GQ_EPI * 8 +
-                8 * (2 * GQ_MAX_STAGES + 9) + 24 + (size_t)(4 + 16) * GQ_EPI + 16;
-    const int need = (qc == 32 && !forced_q) ? 3 : 2;
-    int uni = union_env ? 1 : 0;
-    if (uni && qc == 8 && fx + (size_t)need * GQ_STAGE > GQ_SMEM_LIMIT) {    // last resort: drop the 4 KB quartile array
-      uni = 0;
-      fx -= (size_t)16 * GQ_EPI;
+  int best_stages = 0;
+  for (int pass = 0; pass < 2 && !found; ++pass) {
+    for (int i = 0; i < 4 && !found; ++i) {
+      const int qc = cands[i];
+      if (forced_q && qc != forced_q) continue;
+      size_t fx = 1024 + (size_t)c.k_blocks * GQ_A_BLOCK + GQ_A_BLOCK + GQ_STAGE + (size_t)qc * GQ_EPI * 8 +
+                  8 * (2 * GQ_MAX_STAGES + 9) + 24 + (size_t)(4 + 16) * GQ_EPI + 16;
+      int uni = union_env ? 1 : 0;
+      if (uni && qc == 8 && fx + (size_t)2 * GQ_STAGE > GQ_SMEM_LIMIT) {    // last resort: drop the 4 KB quartile array
+        uni = 0;
+        fx -= (size_t)16 * GQ_EPI;
+      }
+      if (fx + (size_t)2 * GQ_STAGE > GQ_SMEM_LIMIT) continue;
+      const int stages = (int)std::min<size_t>(GQ_MAX_STAGES, (GQ_SMEM_LIMIT - fx) / GQ_STAGE);
+      if (pass == 0) {
+        best_stages = std::max(best_stages, stages);
+        if (stages < 3 && !forced_q) continue;
+      } else if (stages < best_stages) {
+        continue;
+      }
+      c.q_cap = qc;
+      c.union_bound = uni;
+      c.stages = stages;
+      c.smem = fx + (size_t)c.stages * GQ_STAGE;
+      found = true;
     }
-    if (fx + (size_t)need * GQ_STAGE > GQ_SMEM_LIMIT) continue;
-    c.q_cap = qc;
-    c.union_bound = uni;
-    c.stages = (int)std::min<size_t>(GQ_MAX_STAGES, (GQ_SMEM_LIMIT - fx) / GQ_STAGE);
-    c.smem = fx + (size_t)c.stages * GQ_STAGE;
-    found = true;
   }
   if (!found) c.ok = false;
   return c;
