@@ -189,6 +189,28 @@ def check_timed_launch(idx, emb, nu, mi, u, i, mode, n_sample=512):
             "against": "fp64 CPU scores of the same propagated embeddings, train items masked"}
 
 
+def check_layer_rows(graph, X, n_rows=64, seed=5):
+    """One SpMM layer of `graph` on X, sampled output rows against an fp64 gather of the exported CSR rows (all on the
+    device, independent of the SpMM kernel).  -> dict for the JSON line."""
+    import torch
+    Y = torch.empty(graph.n_rows, X.shape[1], device=X.device)
+    graph.spmm(X, Y=Y)
+    e = graph.export()
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    rows = torch.randint(0, graph.n_rows, (n_rows,), generator=gen).to(X.device)
+    rows = torch.cat([rows, e["row_order"][:2].long(), e["row_order"][-2:].long()])       # + the longest and shortest rows
+    worst = 0.0
+    for r in rows.tolist():
+        a, b = int(e["indptr"][r]), int(e["indptr"][r + 1])
+        terms = e["values"][a:b].double()[:, None] * X[e["indices"][a:b].long()].double()
+        ref = terms.sum(0)
+        scale = terms.abs().sum(0).max().item() + 1e-30
+        worst = max(worst, (Y[r].double() - ref).abs().max().item() / scale)
+    del e, Y
+    return {"ok": worst <= 1e-5, "rows_checked": int(rows.numel()), "max_rel_err": worst, "tolerance": 1e-5,
+            "against": "fp64 gather of the exported CSR rows (torch, on the device)"}
+
+
 def north_star_scale_leg(args, rank, world_size, dev, dist):
     """configs[3]: 10 M users / 2 M items / 1e9 edges, d = 128, 3 layers; row-sharded with the fused peer-store
     exchange at N > 1.  Returns the dict for the JSON line (or {'error': ...})."""
@@ -210,6 +232,7 @@ def north_star_scale_leg(args, rank, world_size, dev, dist):
             engine = parallel.ShardedEngine(g, nu, mi, d, N_LAYERS, rank, world_size, dev, propagate=args.propagate)
             del g
             torch.cuda.empty_cache()
+            engine.propagate(E0)                      # fills engine.X[0] with the relabelled layer-0 embeddings
             run = lambda: engine.propagate(E0)
             mode = engine.mode
         else:
@@ -217,6 +240,14 @@ def north_star_scale_leg(args, rank, world_size, dev, dist):
             out = torch.empty_like(E0)
             run = lambda: g.propagate_fwd(E0, N_LAYERS, out=out)
             mode = "single GPU"
+        # parity at this shape: one layer of the graph this rank propagates (its row shard at N > 1), sampled rows
+        if engine is None:
+            parity = check_layer_rows(g, E0)
+        elif getattr(engine, "local", None) is not None:
+            parity = check_layer_rows(engine.local, engine.X[0])
+        else:
+            parity = check_layer_rows(engine.g_full, E0)
+        torch.cuda.empty_cache()
         for _ in range(2):
             run()
         if dist is not None:
@@ -240,7 +271,7 @@ def north_star_scale_leg(args, rank, world_size, dev, dist):
         res = {"workload": args.scale_workload, "n_users": nu, "m_items": mi, "edges": E, "d": d, "layers": N_LAYERS,
                "n_gpus": world_size, "mode": mode, "ms_propagate": ms, "edges_per_s": N_LAYERS * nnz / (ms * 1e-3),
                "hbm_gbs_per_gpu_algorithmic": layer_bytes / world_size / (ms / N_LAYERS * 1e-3) / 1e9,
-               "graph_build_s_per_rank": build_s, "timing": "CUDA events, max over ranks, 3 repetitions after 2 warm-ups; "
+               "parity_rank0": parity, "graph_build_s_per_rank": build_s, "timing": "CUDA events, max over ranks, 3 repetitions after 2 warm-ups; "
                "the graph (8 GB of indices) is far larger than L2"}
         if engine is not None:
             engine.close()

@@ -29,6 +29,8 @@ _SIGS = {
     "lgx_graph_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "lgx_graph_export": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "lgx_graph_pointers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "lgx_graph_get_flags": (C.c_int, [_P]),
+    "lgx_graph_set_flags": (C.c_int, [_P, C.c_int32]),
     "lgx_graph_destroy": (C.c_int, [_P]),
     "lgx_spmm_workspace_bytes": (C.c_size_t, [_P, C.c_int32]),
     "lgx_spmm": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_int32, _P, _P]),
@@ -154,6 +156,15 @@ class Graph:
             check(lib().lgx_graph_from_csr(indptr.numel() - 1, n_cols, indices.numel(), ptr(indptr), ptr(indices),
                                            ptr(values), n_users, m_items, chunk_nnz, stream(), C.byref(out)))
         return Graph(out.value, indptr.device)
+
+    @property
+    def normalized(self) -> bool:
+        """every value == dinv[row] * dinv[col] (graphs built from unique pairs)"""
+        return bool(lib().lgx_graph_get_flags(self.handle) & 1)
+
+    def assume_normalized(self, flag: bool = True):
+        """declare that an adopted CSR (from_csr) is a row block of a normalised adjacency"""
+        check(lib().lgx_graph_set_flags(self.handle, 1 if flag else 0))
 
     def __del__(self):
         try:

@@ -104,6 +104,9 @@ struct lgx_graph {
   //             columns -- [n_hot table slots][cold column ids], values alongside, work items with len | n_hot << 16
   //             (built on first use for the table size that fits the embedding width; rebuilt if another width asks
   //             for another size)
+  // degree above which a column counts as hot for the SpMM's L2 residency hints, per embedding width class
+  // (d <= 32, 64, 128, 256, 512): the rows that qualify fill about 72 MB of L2
+  int32_t hot_deg[5] = {0, 0, 0, 0, 0};
   int32_t* hot_ids = nullptr;
   int32_t n_hot = 0;
   int64_t hot_cover[6] = {0, 0, 0, 0, 0, 0};

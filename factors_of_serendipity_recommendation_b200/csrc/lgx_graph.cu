@@ -259,7 +259,20 @@ static int build_schedule(lgx_graph* g, int32_t chunk_nnz, cudaStream_t st) {
   SCHED_CUDA(cudaMemcpyAsync(&totals[1], n_part + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   SCHED_CUDA(cudaMemcpyAsync(&totals[2], is_long + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   if (n > 0) SCHED_CUDA(cudaMemcpyAsync(&max_len, len_sorted, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  // hot-degree thresholds for the L2 hints: the row lengths at the ranks where the hottest rows fill ~72 MB.  A row
+  // shard (n_rows < n_cols, degree-cyclic deal) sees every n_cols / n_rows-th row of the global order.
+  uint32_t hot_len[5] = {0, 0, 0, 0, 0};
+  if (n > 0) {
+    const int widths[5] = {32, 64, 128, 256, 512};
+    for (int j = 0; j < 5; ++j) {
+      static const double budget = [] { const char* e = std::getenv("LGX_SPMM_L2_MB"); return (e ? std::atof(e) : 72.0) * 1e6; }();
+      const double h_global = budget / (widths[j] * 4.0);
+      const int64_t rank = std::min<int64_t>(n - 1, (int64_t)(h_global * (double)n / (double)std::max<int64_t>(1, g->n_cols)));
+      SCHED_CUDA(cudaMemcpyAsync(&hot_len[j], len_sorted + rank, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+  }
   SCHED_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < 5; ++j) g->hot_deg[j] = (int32_t)hot_len[j];
   g->n_work = totals[0];
   g->n_partials = totals[1];
   g->n_long = totals[2];
@@ -586,6 +599,16 @@ int lgx_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_
     return rc;
   }
   *out = g;
+  return LGX_OK;
+}
+
+int lgx_graph_get_flags(const lgx_graph* g) {
+  return g && g->values_are_dinv_products ? LGX_GRAPH_NORMALIZED : 0;
+}
+
+int lgx_graph_set_flags(lgx_graph* g, int32_t flags) {
+  LGX_REQUIRE(g != nullptr, "graph is NULL");
+  g->values_are_dinv_products = (flags & LGX_GRAPH_NORMALIZED) != 0;
   return LGX_OK;
 }
 

@@ -198,15 +198,64 @@ k_spmm(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, co
 // -- the gather loop was instruction-bound, not memory-bound.)
 // MODE bit 0: peer output (fused all-gather), bit 1: edge dropout.  Separate instantiations: with runtime
 // flags the plain path lost 4% (peer check per row) + 5% (dropout check per index batch).
+// MODE bit 2: L2 residency hints for graphs whose embedding table is far larger than L2 (synth-1b: 6 GB of rows, every
+// non-zero pulled a 512-byte row from HBM = 36x the algorithmic bytes).  The gather of a HOT column (degree >= the
+// graph's hot_deg: value = dinv[row] * dinv[col] <= dinv[row] / sqrt(hot_deg), no lookup needed) is issued with an
+// L2 evict_last policy, every other gather and the index / value streams with evict_first, so the ~70 MB of rows that
+// take most of the gathers stay in the 126 MB L2 instead of being flushed by the cold stream between two uses.
+__device__ __forceinline__ float4 ld_gather_f4_policy(const float4* p, uint64_t pol) {
+  float4 r;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int32_t ld_stream_i32_policy(const int32_t* p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32_policy(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_f4_policy(float* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+// epilogue4 with every access marked evict_first: the layer's outputs (and the running sum) are streamed once
+__device__ __forceinline__ float4 epilogue4_stream(float4 acc, int64_t off, const float* S_in, float* __restrict__ Y,
+                                                   float* S_out, float div, uint64_t pol) {
+  if (Y) st_f4_policy(Y + off, acc, pol);
+  float4 s = acc;
+  if (S_out) {
+    s = ld_gather_f4_policy(reinterpret_cast<const float4*>(S_in + off), pol);
+    s.x += acc.x; s.y += acc.y; s.z += acc.z; s.w += acc.w;
+    if (div != 1.0f) {
+      s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div); s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
+    }
+    st_f4_policy(S_out + off, s, pol);
+  }
+  return s;
+}
+struct L2Hint {
+  const float* dinv;     // per row of this graph
+  float hot_rsqrt;       // 1 / sqrt(hot degree)
+};
 template <int G, int V, int U, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB)
 k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partials, const int32_t* __restrict__ indices,
              const float* __restrict__ values, const float* __restrict__ X, const float* S_in,
              float* __restrict__ Y, float* S_out, float* __restrict__ partial, float div, const PeerOut po,
-             const DropSpec drop) {
+             const DropSpec drop, const L2Hint l2h) {
   constexpr int D4 = G * V;            // float4 per embedding row
   constexpr int D = 4 * D4;
   constexpr int UU = U > G ? G : U;
+  uint64_t pol_hot = 0, pol_cold = 0;
+  if (MODE & 4) {
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+  }
   const int lig = threadIdx.x & (G - 1);
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -230,6 +279,8 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
     int maxlen = len;
 #pragma unroll
     for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    float hot_thr = 0.f;
+    if (MODE & 4) hot_thr = have ? __ldg(l2h.dinv + row) * l2h.hot_rsqrt : 0.f;
 
     float4 acc[V];
 #pragma unroll
@@ -238,8 +289,8 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
     int32_t c_nxt = 0;
     float a_nxt = 0.f;
     if (lig < len) {
-      c_nxt = ld_stream_i32(ci + lig);
-      a_nxt = ld_stream_f32(cv + lig);
+      c_nxt = (MODE & 4) ? ld_stream_i32_policy(ci + lig, pol_cold) : ld_stream_i32(ci + lig);
+      a_nxt = (MODE & 4) ? ld_stream_f32_policy(cv + lig, pol_cold) : ld_stream_f32(cv + lig);
       if (MODE & 2) a_nxt = drop_value(drop, start + lig, a_nxt);
     }
     for (int base = 0; base < maxlen; base += G) {
@@ -248,8 +299,8 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
       const int kn = base + G + lig;
       c_nxt = 0; a_nxt = 0.f;
       if (kn < len) {
-        c_nxt = ld_stream_i32(ci + kn);
-        a_nxt = ld_stream_f32(cv + kn);
+        c_nxt = (MODE & 4) ? ld_stream_i32_policy(ci + kn, pol_cold) : ld_stream_i32(ci + kn);
+        a_nxt = (MODE & 4) ? ld_stream_f32_policy(cv + kn, pol_cold) : ld_stream_f32(cv + kn);
         if (MODE & 2) a_nxt = drop_value(drop, start + kn, a_nxt);
       }
       const int cnt = len - base;
@@ -264,7 +315,11 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
             const uint32_t cj = (uint32_t)__shfl_sync(0xffffffffu, c, j0 + j, G);
             av[j] = __shfl_sync(0xffffffffu, a, j0 + j, G);
 #pragma unroll
-            for (int v = 0; v < V; ++v) x[j][v] = __ldg(X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G)));
+            for (int v = 0; v < V; ++v) {
+              const float4* src = X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G));
+              if (MODE & 4) x[j][v] = ld_gather_f4_policy(src, av[j] <= hot_thr ? pol_hot : pol_cold);
+              else x[j][v] = __ldg(src);
+            }
           }
 #pragma unroll
           for (int j = 0; j < UU; ++j)
@@ -285,7 +340,11 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
 #pragma unroll
             for (int v = 0; v < V; ++v) {
               x[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (j0 + j < cnt) x[j][v] = __ldg(X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G)));
+              if (j0 + j < cnt) {
+                const float4* src = X4 + (cj * (uint32_t)D4 + (uint32_t)(v * G));
+                if (MODE & 4) x[j][v] = ld_gather_f4_policy(src, av[j] <= hot_thr ? pol_hot : pol_cold);
+                else x[j][v] = __ldg(src);
+              }
             }
           }
 #pragma unroll
@@ -302,7 +361,8 @@ k_spmm_fixed(const WorkItem* __restrict__ work, int64_t n_work, int64_t n_partia
         if (part >= 0) {
           *reinterpret_cast<float4*>(partial + (int64_t)part * D + col) = acc[v];
         } else {
-          const float4 mean = epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
+          const float4 mean = (MODE & 4) ? epilogue4_stream(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div, pol_cold)
+                                         : epilogue4(acc[v], (int64_t)row * D + col, S_in, Y, S_out, div);
           if (MODE & 1) peer_store4(po, row, D, col, acc[v], mean);
         }
       }
@@ -532,6 +592,19 @@ static void launch_spmm(const lgx_graph* g, const float* X, const float* S_in, f
                                                            X, S_in, Y, S_out, partial, div, d, g->dinv, hot_rsqrt, drop);
 }
 
+// L2 hints: only where the table cannot live in L2 anyway (> 2x its size), the graph knows its rows' dinv and
+// value == dinv[row] * dinv[col] (LGX_SPMM_L2HINT=0 switches them off, =1 forces them for experiments).
+static int hot_degree_for(const lgx_graph* g, int d) {
+  const int j = d <= 32 ? 0 : (d <= 64 ? 1 : (d <= 128 ? 2 : (d <= 256 ? 3 : 4)));
+  return g->hot_deg[j];
+}
+static bool use_l2_hints(const lgx_graph* g, int d) {
+  static const int forced = [] { const char* e = getenv("LGX_SPMM_L2HINT"); return e ? atoi(e) : -1; }();
+  if (forced == 0 || !g->values_are_dinv_products || g->dinv == nullptr || hot_degree_for(g, d) <= 0) return false;
+  if (forced == 1) return true;
+  return (double)g->n_cols * d * 4.0 > 2.0 * 126e6;
+}
+
 template <int G, int V, int U, int MINB, int MODE>
 static void launch_fixed_t(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
                            float div, cudaStream_t st, const PeerOut& po, const DropSpec& drop) {
@@ -540,13 +613,36 @@ static void launch_fixed_t(const lgx_graph* g, const float* X, const float* S_in
   const int64_t groups_per_block = 256 / G;
   const int64_t need = (g->n_work + groups_per_block - 1) / groups_per_block;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, max_blocks));
+  L2Hint l2h{g->dinv, 0.f};
+  if (MODE & 4) {
+    l2h.hot_rsqrt = 1.0f / sqrtf((float)std::max(1, hot_degree_for(g, 4 * G * V)));
+    // Optional persisting carve-out (LGX_SPMM_L2_PERSIST_MB, default off): measured on the 1B-edge graph it HURTS
+    // (428 ms for 3 layers with 80 MB set aside vs 405 ms with the hints alone and 422 ms without hints) -- the
+    // carve-out takes L2 away from the cold stream without keeping more of the hot rows.
+    static bool carved[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < kMaxDevices && !carved[dev]) {
+      int max_persist = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      static const double want_mb = [] { const char* e = getenv("LGX_SPMM_L2_PERSIST_MB"); return e ? atof(e) : 0.0; }();
+      const size_t want = (size_t)std::min<double>((double)max_persist, want_mb * 1e6);
+      if (want > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaGetLastError();
+      carved[dev] = true;
+    }
+  }
   k_spmm_fixed<G, V, U, MINB, MODE><<<blocks, 256, 0, st>>>(g->work, g->n_work, g->n_partials, g->indices, g->values, X,
-                                                           S_in, Y, S_out, partial, div, po, drop);
+                                                           S_in, Y, S_out, partial, div, po, drop, l2h);
 }
 template <int G, int V, int U, int MINB>
 static void launch_fixed(const lgx_graph* g, const float* X, const float* S_in, float* Y, float* S_out, float* partial,
                          float div, cudaStream_t st, const PeerOut& po, const DropSpec& drop) {
   const int mode = (po.n > 0 ? 1 : 0) | (drop.enabled ? 2 : 0);
+  if (!drop.enabled && use_l2_hints(g, 4 * G * V)) {
+    if (mode == 0) launch_fixed_t<G, V, U, MINB, 4>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+    else launch_fixed_t<G, V, U, MINB, 5>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
+    return;
+  }
   if (mode == 0) launch_fixed_t<G, V, U, MINB, 0>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
   else if (mode == 1) launch_fixed_t<G, V, U, MINB, 1>(g, X, S_in, Y, S_out, partial, div, st, po, drop);
   else if (mode == 2) launch_fixed_t<G, V, U, MINB, 2>(g, X, S_in, Y, S_out, partial, div, st, po, drop);

@@ -195,6 +195,8 @@ class ShardedEngine:
             self.copy_stream = torch.cuda.Stream(device=device)
         else:
             self.local = _lgx.Graph.from_csr(ptr, cols, vals, n_cols=world * self.n_local, n_users=0, m_items=0)
+            if graph.normalized:
+                self.local.assume_normalized()          # a row block of D^-1/2 A D^-1/2: enables the SpMM's L2 hints
         del ptr, cols, vals
         self.gather_src = self.old_of_new.clamp(min=0)
         self.pad_mask = (self.old_of_new < 0)
@@ -229,6 +231,15 @@ class ShardedEngine:
         ptr, cols, vals, self.n_local, self.new_id, self.old_of_new, self.degree = build_local_csr(
             n_users, m_items, users_part.to(device), items_part.to(device), rank, world)
         self.local = _lgx.Graph.from_csr(ptr, cols, vals, n_cols=world * self.n_local, n_users=0, m_items=0)
+        # unique pairs <=> row length == degree for every row: then every value is dinv[row] * dinv[col]
+        rl = (ptr[1:] - ptr[:-1])
+        mine_old = self.old_of_new[rank * self.n_local:(rank + 1) * self.n_local]
+        unique_here = torch.tensor([int((rl == self.degree[mine_old.clamp(min=0)] * (mine_old >= 0)).all().item())],
+                                   device=device)
+        if world > 1:
+            dist.all_reduce(unique_here, op=dist.ReduceOp.MIN)
+        if bool(unique_here.item()):
+            self.local.assume_normalized()
         del ptr, cols, vals
         self.gather_src = self.old_of_new.clamp(min=0)
         self.pad_mask = (self.old_of_new < 0)

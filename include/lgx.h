@@ -81,6 +81,13 @@ int lgx_graph_export(const lgx_graph* g, int64_t* indptr, int32_t* indices, floa
  * sparse_csr tensor for getSparseGraph() without a copy. */
 int lgx_graph_pointers(const lgx_graph* g, const int64_t** indptr, const int32_t** indices,
                        const float** values);
+/* LGX_GRAPH_NORMALIZED: every stored value equals dinv[row] * dinv[col] with dinv = (row length)^-1/2 -- true for
+ * lgx_graph_build graphs without duplicate pairs.  lgx_graph_from_csr cannot know it: a caller that adopts a row block
+ * of such a graph (row-sharded propagation) sets the flag, which lets the SpMM classify hot columns from the value
+ * alone (L2 residency hints on graphs whose embedding table is far larger than L2). */
+#define LGX_GRAPH_NORMALIZED 1
+int lgx_graph_get_flags(const lgx_graph* g);
+int lgx_graph_set_flags(lgx_graph* g, int32_t flags);
 int lgx_graph_destroy(lgx_graph* g);
 
 /* ----------------------------------------------------------------------------------- propagation
