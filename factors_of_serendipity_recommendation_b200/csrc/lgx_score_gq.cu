@@ -373,7 +373,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, GQ_EPI);
+      mbar_init(bar_tempty + 8 * b, GQ_EPI / 32);     // one arrival per epilogue warp
       mbar_init(bar_mfull + 8 * b, 1);
       mbar_init(bar_mfree + 8 * b, 1);
     }
@@ -696,7 +696,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       const int gid_base = ((t_begin + it) * GQ_TILE_I + h * 128) / GQ_GROUP;
       if (p.dbg & 2) {                        // experiment: barrier handshake only (TMA / MMA / builder floor)
         tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * buf);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         continue;
       }
       const float th = (p.dbg & 1) ? CUDART_INF_F : st.filter();   // experiment 1: loads + max tree, nothing appended
@@ -716,7 +717,10 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       LGX_TMEM_LD32(va, taddr + 96);
       LGX_TMEM_WAIT(va);
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);      // the whole tile half is in registers: the TMEM buffer may be overwritten
+      __syncwarp();
+      // ONE arrival per warp: 256 per-thread arrivals are 256 serialised shared-memory atomics on the path that
+      // hands the accumulator buffer back to the MMA warp (the round trip that bounds this kernel)
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);      // the whole tile half is in registers
       LGX_KEEP(vb);
       LGX_KEEP(vc);
       gq_chunk<KMAX, SHARE>(vb, gid_base + 4, st, th);
