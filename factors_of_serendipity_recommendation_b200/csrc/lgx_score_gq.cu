@@ -50,7 +50,17 @@ constexpr int GQ_EPI = 256;                     // epilogue threads
 constexpr int GQ_THREADS = 128 + GQ_EPI;
 constexpr int GQ_MAX_STAGES = 6;
 constexpr int GQ_TMEM_BUF = 256;
-constexpr int GQ_GROUP = 8;                     // columns per candidate group
+#ifndef LGX_GQ_GROUP
+#define LGX_GQ_GROUP 8
+#endif
+#ifndef LGX_GQ_DRAIN
+#define LGX_GQ_DRAIN 2         // queue entries inserted per lane per check once a lane holds LGX_GQ_LOW (0: only full flushes)
+#endif
+#ifndef LGX_GQ_LOW
+#define LGX_GQ_LOW 4
+#endif
+constexpr int GQ_GROUP = LGX_GQ_GROUP;          // columns per candidate group (4 or 8): 4 halves the rescoring work for
+                                                // twice the (cheap, predicated) appends of an epilogue that mostly waits
 constexpr int GQ_SMEM_LIMIT = 232448;
 constexpr uint32_t GQ_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GQ_TILE_I >> 3) << 17) |
                               ((uint32_t)(GQ_TILE_U >> 4) << 24);
@@ -63,6 +73,7 @@ struct GqParams {
   int q_cap;
   int union_bound;
   int n_splits, tiles_per_split;
+  int cl;                 // CTAs per cluster sharing every B tile by TMA multicast (1 = no cluster)
   int has_mask;
   int dbg;                // LGX_GQ_DEBUG (experiments): 1 = TMEM loads only, 2 = no TMEM loads either, 4 = no mask,
                           // 8 = masks built but no mask MMA issued, 32 = no pre-bucketing (in-kernel list walk)
@@ -244,7 +255,9 @@ template <int KMAX, bool SHARE>
 struct GqEpi {
   float lv[KMAX];
   int32_t li[KMAX];
-  float* qhead; float* qbase;
+  uint32_t qb;            // shared-memory address of this thread's queue slot 0; slot n at qb + n * ROWB
+  int qn, qh;             // queue slots [qh, qn) hold candidates not yet inserted (FIFO; both reset when it empties)
+  static constexpr uint32_t ROWB = GQ_EPI * 8;
   float* thr_mine; const float* thr_other;
   float4* quart_mine; const float4* quart_other;
   float tu;
@@ -262,12 +275,14 @@ struct GqEpi {
     }
     tu = -CUDART_INF_F;
   }
+  // One 8-byte store per candidate at an address derived from the COUNT: the store's address register is never
+  // overwritten (a pointer bumped after every store made each predicated bump wait for the store to read it).
   __device__ __forceinline__ void append(float s, int32_t j) {
-    qhead[0] = s;
-    reinterpret_cast<int32_t*>(qhead)[GQ_EPI] = j;
-    qhead += ROW;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(qb + (uint32_t)qn * ROWB), "f"(s), "r"(j) : "memory");
+    ++qn;
   }
-  __device__ __forceinline__ bool fuller_than(int rows) const { return qhead > qbase + rows * ROW; }
+  __device__ __forceinline__ bool fuller_than(int rows) const { return qn > rows; }
+  __device__ __forceinline__ bool pending_at_least(int n) const { return qn - qh >= n; }
   // groups reach a thread in ascending id order, so an equal maximum loses the tie: strict '>'
   __device__ __forceinline__ void insert(float x, int32_t xi) {
 #pragma unroll
@@ -280,10 +295,31 @@ struct GqEpi {
     lv[0] = g0 ? x : lv[0];
     li[0] = g0 ? xi : li[0];
   }
+  __device__ __forceinline__ void pop_insert() {
+    float x;
+    int32_t xi;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(x), "=r"(xi) : "r"(qb + (uint32_t)qh * ROWB) : "memory");
+    insert(x, xi);
+    ++qh;
+  }
+  // everything queued (warp-convergent call; lanes run their own counts)
   __device__ __forceinline__ void flush() {
+    while (qh < qn) pop_insert();
+    qh = qn = 0;
+    publish();
+  }
+  // at most `iters` candidates per lane: one lane's long queue no longer makes its warp (and through the accumulator
+  // hand-back, the whole pipeline) wait for a 16-deep insertion burst
+  __device__ __forceinline__ void drain(int iters) {
+    for (int r = 0; r < iters; ++r) {
+      if (qh < qn) pop_insert();
+      if (!__any_sync(0xffffffffu, qh < qn)) break;
+    }
+    if (qh == qn) qh = qn = 0;
+    publish();
+  }
+  __device__ __forceinline__ void publish() {
     const unsigned gb = (SHARE && gbound) ? *reinterpret_cast<const volatile unsigned*>(gbound) : 0u;
-    for (const float* a = qbase; a < qhead; a += ROW) insert(a[0], reinterpret_cast<const int32_t*>(a)[GQ_EPI]);
-    qhead = qbase;
     float t = lv[KMAX - 1];
     if (use_union) {
       const float a1 = lv[KMAX / 4 - 1], a2 = lv[KMAX / 2 - 1], a3 = lv[3 * KMAX / 4 - 1];
@@ -309,14 +345,46 @@ struct GqEpi {
 // past the end, filled by TMA) are ignored by max and fail '>'.
 template <int KMAX, bool SHARE>
 __device__ __forceinline__ void gq_chunk(const uint32_t (&v)[32], int gid0, GqEpi<KMAX, SHARE>& st, float th) {
+  if (GQ_GROUP == 8) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float a = max3(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
-    const float b = max3(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-    const float m = max3(a, b, fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-    if (m > th) st.append(m, gid0 + g);
+    for (int g = 0; g < 4; ++g) {
+      const float a = max3(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+      const float b = max3(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+      const float m = max3(a, b, fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+      if (m > th) st.append(m, gid0 + g);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float m = fmaxf(max3(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2])),
+                            __uint_as_float(v[4 * g + 3]));
+      if (m > th) st.append(m, gid0 + g);
+    }
   }
 }
+
+#ifdef LGX_GQ_PROF
+// Diagnostic build only (-DLGX_GQ_PROF, never shipped): cycle counters summed over all CTAs and tiles.
+//  0 mma: wait3 cycles   1 mma: mask-part cycles   2 mma: real-issue cycles   3 mma: tempty not ready at first poll
+//  4 mma: mfull not ready   5 mma: full not ready   6 tiles
+//  8 epi(warp 0): wait tfull   9 epi: tfull -> tempty arrive   10 epi: arrive -> tile done
+//  12 builder: reclaim wait   13 builder: rest   16 tma: wait empty
+__device__ unsigned long long gq_prof[32];
+// timeline of one CTA (blockIdx.x == 7), tiles [GQ_TR0, GQ_TR0 + 64): [role 0..11][tile][event 0..5] = clock64
+constexpr int GQ_TR0 = 120;
+__device__ long long gq_trace[12 * 64 * 6];
+#define PROF_T(x) const long long x = clock64()
+#define PROF_ADD(i, v) (prof_acc[i] += (unsigned long long)(v))
+#define TRACE(role, it, ev, t)                                                                     \
+  do {                                                                                             \
+    if (blockIdx.x == 7 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (it) >= GQ_TR0 && (it) < GQ_TR0 + 64) \
+      gq_trace[((role) * 64 + ((it) - GQ_TR0)) * 6 + (ev)] = (t);                                   \
+  } while (0)
+#else
+#define PROF_T(x)
+#define PROF_ADD(i, v)
+#define TRACE(role, it, ev, t)
+#endif
 
 template <int KMAX, bool SMALLQ, bool SHARE>
 __global__ void __launch_bounds__(GQ_THREADS, 1)
@@ -360,6 +428,21 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   const int n_tiles = (p.M + GQ_TILE_I - 1) / GQ_TILE_I;
   const int t_begin = split * p.tiles_per_split;
   const int n_my = max(0, min(n_tiles, t_begin + p.tiles_per_split) - t_begin);
+  // Cluster mode (p.cl = 2 or 4 CTAs along x: neighbouring user tiles, the same item tiles): CTA r loads rows
+  // [r, r + 1) * 256 / cl of every B tile and TMA multicasts them into all cl CTAs, so a tile leaves the L2 once per
+  // cluster instead of once per CTA -- the B stream out of the L2 (32 KB per 512 tensor cycles per SM) is what the
+  // pipeline waits for at d = 64.  A ring stage is free again when ALL cl consumers have retired it: every MMA warp's
+  // commit arrives on the stage's empty barrier of every CTA.  `live` is false for the CTAs that pad an uneven
+  // user-tile count: they load their share and release stages, nothing else.
+  const bool mc = p.cl > 1 && !(p.dbg & 128);              // experiment 128: cluster launch, unicast loads
+  const uint32_t cta_rank = mc ? cluster_ctarank() : 0u;
+  const uint16_t mc_mask = (uint16_t)((1u << p.cl) - 1u);
+  const uint32_t mc_rows = (uint32_t)GQ_TILE_I / (uint32_t)(mc ? p.cl : 1);
+  const bool live = u_tile * GQ_TILE_U < p.B;
+#ifdef LGX_GQ_PROF
+  unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long pstart = clock64();
+#endif
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_u)) : "memory");
@@ -368,7 +451,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, mc ? p.cl : 1);
     }
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) {
@@ -396,13 +479,14 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();           // the peers' barriers exist before anything of ours can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (n_my > 0) {
+    if (n_my > 0 && (live || mc)) {
       // ---------------------------------------------------------------- TMA producer (converged warp, one lane issues)
-      if (elect_one()) {
+      if (live && elect_one()) {
         mbar_expect_tx(bar_a, (uint32_t)p.k_blocks * GQ_A_BLOCK);
         for (int kb = 0; kb < p.k_blocks; ++kb)
           tma_load_2d(sA + kb * GQ_A_BLOCK, &tmap_u, bar_a, kb * GQ_KBLK, u_tile * GQ_TILE_U);
@@ -413,22 +497,44 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       for (int it = 0; it < n_my; ++it) {
         const int row0 = (t_begin + it) * GQ_TILE_I;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          PROF_T(tw0);
           mbar_wait<false>(bar_empty + 8 * stage, phase ^ 1);
+          PROF_T(tw1);
+          PROF_ADD(0, tw1 - tw0);
           if (elect_one()) {
-            mbar_expect_tx(bar_full + 8 * stage, GQ_STAGE);
-            tma_load_2d(sB + stage * GQ_STAGE, &tmap_i, bar_full + 8 * stage, kb * GQ_KBLK, row0);
+            mbar_expect_tx(bar_full + 8 * stage, GQ_STAGE);         // our rows + the peers' (which may land first)
+            if (mc)
+              tma_load_2d_mc(sB + stage * GQ_STAGE + cta_rank * mc_rows * 128u, &tmap_i, bar_full + 8 * stage,
+                             kb * GQ_KBLK, row0 + (int)(cta_rank * mc_rows), mc_mask);
+            else
+              tma_load_2d(sB + stage * GQ_STAGE, &tmap_i, bar_full + 8 * stage, kb * GQ_KBLK, row0);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
+#ifdef LGX_GQ_PROF
+      if (lane == 0) atomicAdd(&gq_prof[16], prof_acc[0]);
+#endif
     }
   } else if (warp == 1) {
-    if (n_my > 0) {
+    if (n_my > 0 && !live) {
+      if (mc) {
+        // padding CTA: the stages it receives are released unread (a commit with no MMA before it arrives at once)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_my * p.k_blocks; ++j) {
+          mbar_wait<false>(bar_full + 8 * stage, phase);
+          if (elect_one()) tc_commit_mc(bar_empty + 8 * stage, mc_mask);
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (n_my > 0) {
       // ---------------------------------------------------------------- MMA issuer (converged warp, one lane issues)
       // This warp is the serial resource of the pipeline: everything it needs per tile is kept in registers and
-      // advanced incrementally (barrier addresses, the B descriptor, phases), the three barriers a tile needs are
-      // polled by three lanes in ONE try_wait, and the tile loop body exists twice so the TMEM buffer is static.
+      // advanced incrementally (barrier addresses, the B descriptor, phases), and the tile loop body exists twice so
+      // the TMEM buffer is static.
       mbar_wait<false>(bar_a, 0);
       tc_fence_after();
       const uint64_t adesc_m = umma_desc_sw128(sAm), bdesc_m = umma_desc_sw128(sBm);
@@ -436,21 +542,44 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       const uint64_t bdesc0 = umma_desc_sw128(sB);
       int stage = 0;
       uint32_t phase = 0;               // parity of the B ring
-      uint32_t mrc = 0u;                // mask rounds consumed: buffer = mrc & 1
-      auto tile = [&](int it, const int buf) {
+      uint32_t mr0 = 0u, mr1 = 0u;      // mask rounds consumed per buffer (tile `it` uses buffer it & 1 = its TMEM buffer)
+      // ready(it): everything tile `it` needs before its first MMA -- its TMEM buffer drained (tempty), its mask round
+      // published (mfull; returns the round's count word) and its first B block landed (full).  All three are
+      // normally complete long before they are looked at, but a completed try_wait still costs ~85 cycles and the
+      // tensor pipe queues only about two MMAs: checked between tiles, the pipe ran dry while this warp polled
+      // (~350 of a tile's ~1 450 cycles).  So tile it + 1 is checked in the MIDDLE of tile it's last K block, behind
+      // two queued MMAs -- unless the ring is so short that the next tile's first block cannot have been requested yet.
+      const bool pipelined = p.stages >= p.k_blocks + 2;
+      auto ready = [&](int it, const int buf, int st, uint32_t ph) -> int {
+        PROF_T(m0);
+        mbar_wait<false>(bar_tempty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);
+        PROF_T(w1);
+        int v = 0;
+        if (p.has_mask) {
+          mbar_wait<false>(bar_mfull + 8 * buf, (buf ? mr1 : mr0) & 1u);
+          v = mcnt[buf];
+        }
+        PROF_T(w2);
+        mbar_wait<false>(bar_full + 8 * st, ph);
+        tc_fence_after();
+        PROF_T(w3);
+        PROF_ADD(0, w3 - m0); PROF_ADD(3, w1 - m0); PROF_ADD(4, w2 - w1); PROF_ADD(5, w3 - w2); PROF_ADD(6, 1);
+        TRACE(0, it, 0, m0); TRACE(0, it, 1, w1); TRACE(0, it, 2, w2); TRACE(0, it, 3, w3);
+        return v;
+      };
+      auto tile = [&](int it, const int buf, int v) -> int {      // returns ready(it + 1) when pipelined
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * GQ_TMEM_BUF;
-        const uint32_t tpar = (uint32_t)((it >> 1) & 1) ^ 1u;
         uint32_t acc = 0u;
+        if (!pipelined) v = ready(it, buf, stage, phase);
+        PROF_T(m2);
         if (p.has_mask) {
           // The tile's train mask first: one K = 16 step per 16 published slots puts -2^100 into the (row, train
           // column) accumulators; the real K steps then accumulate on top.  Mask first, so a buffer is released as
           // soon as its own MMAs retire instead of behind the tile's real MMAs.
-          uint32_t b = mrc & 1u;
-          mbar_wait3(bar_tempty + 8 * buf, tpar, bar_mfull + 8 * b, (mrc >> 1) & 1u, bar_full + 8 * stage, phase, lane);
-          tc_fence_after();
+          const uint32_t b = (uint32_t)buf;
+          uint32_t mr = buf ? mr1 : mr0;
           for (;;) {
-            ++mrc;
-            const int v = mcnt[b];
+            ++mr;
             const int n = v & 255;
             if (elect_one()) {
               if (n > 0) tc_mma_f16(tmem_d, adesc_m + (uint64_t)(4 * b), bdesc_m + (uint64_t)(4 * b), GQ_IDESC, acc);
@@ -460,52 +589,87 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             __syncwarp();
             if (n > 0) acc = 1u;
             if (!(v >> 8)) break;
-            b = mrc & 1u;                 // a tile with more than 32 dirty rows: further rounds
-            mbar_wait<false>(bar_mfull + 8 * b, (mrc >> 1) & 1u);
+            mbar_wait<false>(bar_mfull + 8 * b, mr & 1u);     // a tile with more than 32 dirty rows: further rounds
             tc_fence_after();
+            v = mcnt[b];
           }
-        } else {
-          mbar_wait3(bar_tempty + 8 * buf, tpar, bar_full + 8 * stage, phase, bar_full + 8 * stage, phase, lane);
-          tc_fence_after();
+          if (buf) mr1 = mr; else mr0 = mr;
         }
+        int v_next = 0;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           if (kb > 0) {
             mbar_wait<false>(bar_full + 8 * stage, phase);
             tc_fence_after();
           }
+          const bool last = kb == p.k_blocks - 1;
+          const uint64_t adesc = adesc0 + (uint64_t)(kb * (GQ_A_BLOCK >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (GQ_STAGE >> 4));
           if (elect_one()) {
-            const uint64_t adesc = adesc0 + (uint64_t)(kb * (GQ_A_BLOCK >> 4));
-            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (GQ_STAGE >> 4));
             tc_mma_f16(tmem_d, adesc, bdesc, GQ_IDESC, acc);
             tc_mma_f16(tmem_d, adesc + 2, bdesc + 2, GQ_IDESC, 1u);
+          }
+          __syncwarp();
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+          if (pipelined && last && it + 1 < n_my) v_next = ready(it + 1, buf ^ 1, nstage, nphase);
+          if (elect_one()) {
             tc_mma_f16(tmem_d, adesc + 4, bdesc + 4, GQ_IDESC, 1u);
             tc_mma_f16(tmem_d, adesc + 6, bdesc + 6, GQ_IDESC, 1u);
-            tc_commit(bar_empty + 8 * stage);
-            if (kb == p.k_blocks - 1) tc_commit(bar_tfull + 8 * buf);   // accumulator tile complete
+            if (mc) tc_commit_mc(bar_empty + 8 * stage, mc_mask);
+            else tc_commit(bar_empty + 8 * stage);
+            if (last) tc_commit(bar_tfull + 8 * buf);   // accumulator tile complete
           }
           __syncwarp();
           acc = 1u;
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          stage = nstage;
+          phase = nphase;
         }
+        PROF_T(m3);
+        PROF_ADD(2, m3 - m2);
+        TRACE(0, it, 4, m2); TRACE(0, it, 5, m3);
+        return v_next;
       };
+      PROF_T(mstart);
+      int v = pipelined ? ready(0, 0, 0, 0u) : 0;
       for (int it = 0; it < n_my; it += 2) {
-        tile(it, 0);
-        if (it + 1 < n_my) tile(it + 1, 1);
+        v = tile(it, 0, v);
+        if (it + 1 < n_my) v = tile(it + 1, 1, v);
       }
+#ifdef LGX_GQ_PROF
+      PROF_T(mend);
+      if (lane == 0) {
+        atomicAdd(&gq_prof[0], prof_acc[0]); atomicAdd(&gq_prof[1], (unsigned long long)(mend - mstart)); atomicAdd(&gq_prof[2], prof_acc[2]);
+        atomicAdd(&gq_prof[3], prof_acc[3]); atomicAdd(&gq_prof[4], prof_acc[4]); atomicAdd(&gq_prof[5], prof_acc[5]);
+        atomicAdd(&gq_prof[6], prof_acc[6]);
+      }
+#endif
     }
   } else if (warp < 4) {
-    // -------------------------------------------------------------------- mask builder (warp 3)
-    if (warp == 3 && p.has_mask && n_my > 0) {
+    // -------------------------------------------------------------------- mask builders (warps 3 and 2)
+    // Tile `it` uses mask buffer it & 1.  With pre-bucketed entries the two warps take alternate tiles, so each owns
+    // one buffer and has two tile periods for a tile's work (one warp needed ~1 600 cycles per tile against a
+    // 2 000-cycle tile period and was the longest chain of the pipeline); the list-walking fallback keeps one
+    // cursor set and runs on warp 3 alone over both buffers.
+    if (p.has_mask && n_my > 0 && live) {
       const unsigned lt = (1u << lane) - 1u;
-      uint32_t rc = 0;                    // rounds published: buffer = rc & 1
+      const int bw = warp == 3 ? 0 : 1;   // builder index
+      uint32_t rc0 = 0, rc1 = 0;          // rounds published per buffer
+#ifdef LGX_GQ_PROF
+      int tr_it = bw;                     // trace only: the tile being built (one round per tile assumed)
+#endif
       // what this lane wrote into buffer b the last time (shared-memory addresses, 0 = nothing), or the whole
       // buffer was written by a multi-pass round and is cleared wholesale
       uint32_t uA0 = 0, uB0 = 0, uA1 = 0, uB1 = 0;
       bool wide0 = false, wide1 = false;
       // zero what the previous use of buffer b wrote; then every lane may write again
       auto reclaim = [&](uint32_t b) {
-        mbar_wait<false>(bar_mfree + 8 * b, ((rc >> 1) & 1u) ^ 1u);     // the MMAs that read this buffer have retired
-        ++rc;
+        PROF_T(b0);
+        mbar_wait<false>(bar_mfree + 8 * b, ((b ? rc1 : rc0) & 1u) ^ 1u);   // the MMAs that read this buffer have retired
+        PROF_T(b1);
+        PROF_ADD(0, b1 - b0);
+        TRACE(1 + bw, tr_it, 0, b0); TRACE(1 + bw, tr_it, 1, b1);
+        if (b) ++rc1; else ++rc0;
         const bool wide = b ? wide1 : wide0;
         if (wide) {
           // both K steps of the buffer, all 384 operand rows: 2 x 2 16-byte chunks per row
@@ -527,11 +691,15 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_mfull + 8 * b);
+#ifdef LGX_GQ_PROF
+        TRACE(1 + bw, tr_it, 2, clock64());
+        tr_it += 2;
+#endif
       };
       const int64_t region = p.mk_region ? p.mk_region[u_tile] : -1;
       if (p.dbg & 16) {                   // experiment 16: handshake only, nothing is built
-        for (int it = 0; it < n_my; ++it) {
-          const uint32_t b = rc & 1u;
+        for (int it = bw; it < n_my; it += 2) {
+          const uint32_t b = (uint32_t)bw;
           reclaim(b);
           publish(b, 0, false);
         }
@@ -557,6 +725,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             if (lane < q.n) q.ent = __ldg(ents + q.e0 + lane);
           }
         };
+        const uint32_t b = (uint32_t)bw;              // this warp's tiles all use its own buffer
         auto process = [&](const Pre& q) {
           const int n_e = q.n, e0 = q.e0;
           const uint32_t ent = q.ent;
@@ -574,7 +743,6 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             const int rank = (ws == 0 ? 0 : (ws == 1 ? c0 : (ws == 2 ? c1 : c2))) + __popc(mw & ((1u << (row & 31)) - 1u));
             const int nrounds = n_dirty > 32 ? (n_dirty + 31) >> 5 : 1;
             for (int r = 0; r < nrounds; ++r) {
-              const uint32_t b = rc & 1u;
               reclaim(b);
               if (valid && (rank >> 5) == r) {
                 const int slot = 32 * (int)b + (rank & 31);
@@ -602,7 +770,6 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), n_dirty = c2 + __popc(m3);
             const int nrounds = n_dirty > 32 ? (n_dirty + 31) >> 5 : 1;
             for (int r = 0; r < nrounds; ++r) {
-              const uint32_t b = rc & 1u;
               reclaim(b);
               for (int cbase = 0; cbase < n_e; cbase += 32) {
                 if (cbase + lane < n_e) {
@@ -622,15 +789,15 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             }
           }
         };
-        fetch(s0, 0);
-        fetch(s1, 1);
-        for (int it = 0; it < n_my; it += 3) {
-          fetch(s2, it + 2);
+        fetch(s0, bw);
+        fetch(s1, bw + 2);
+        for (int it = bw; it < n_my; it += 6) {
+          fetch(s2, it + 4);
           process(s0);
-          if (it + 1 < n_my) { fetch(s0, it + 3); process(s1); }
-          if (it + 2 < n_my) { fetch(s1, it + 4); process(s2); }
+          if (it + 2 < n_my) { fetch(s0, it + 6); process(s1); }
+          if (it + 4 < n_my) { fetch(s1, it + 8); process(s2); }
         }
-      } else {
+      } else if (bw == 0) {
         // ---- fallback: walk the 128 sorted train lists here (4 rows per lane, one dependent load per train item)
         GqCursor cur[4];
 #pragma unroll
@@ -651,8 +818,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             n += __popc(bal);
           }
           const int nrounds = n > 32 ? (n + 31) >> 5 : 1;
+          const uint32_t b = (uint32_t)(it & 1);
           for (int r = 0; r < nrounds; ++r) {
-            const uint32_t b = rc & 1u;
             reclaim(b);
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
@@ -671,7 +838,13 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         }
       }
     }
-  } else {
+#ifdef LGX_GQ_PROF
+    if (p.has_mask && n_my > 0 && live && lane == 0) {
+      atomicAdd(&gq_prof[12], prof_acc[0]);
+      atomicAdd(&gq_prof[13], (unsigned long long)(clock64() - pstart));
+    }
+#endif
+  } else if (live) {
     // ------------------------------------------------------------------ epilogue (256 threads)
     const int q = hw_warp & 3;                // TMEM lane quarter this warp may access (hardware warp id % 4)
     const int h = hw_warp >> 2;               // which 128-column half of the tile
@@ -679,7 +852,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     const int col = h * GQ_TILE_U + row;
     GqEpi<KMAX, SHARE> st;
     st.init(p.K);
-    st.qbase = st.qhead = reinterpret_cast<float*>(gbase + off_queue) + col;
+    st.qb = base + off_queue + (uint32_t)col * 8u;
+    st.qn = st.qh = 0;
     st.thr_mine = thr_all + col;
     st.thr_other = thr_all + (h ^ 1) * GQ_TILE_U + row;
     st.quart_mine = quart_all + col;
@@ -690,8 +864,12 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
     const int u = u_tile * GQ_TILE_U + row;
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
+      PROF_T(e0);
       mbar_wait<false>(bar_tfull + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      PROF_T(e1);
+      PROF_ADD(0, e1 - e0);
+      TRACE(4 + hw_warp, it, 0, e0); TRACE(4 + hw_warp, it, 1, e1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GQ_TMEM_BUF + h * 128);
       const int gid_base = ((t_begin + it) * GQ_TILE_I + h * 128) / GQ_GROUP;
       if (p.dbg & 2) {                        // experiment: barrier handshake only (TMA / MMA / builder floor)
@@ -713,6 +891,18 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       LGX_TMEM_WAIT(va);
       LGX_KEEP(vb);
       LGX_KEEP(vc);
+      // flush checks: a lane appends at most APC = 32 / GQ_GROUP candidates per chunk; small queues are checked with
+      // a margin of 8 appends, deep ones with a margin of 16
+      constexpr int APC = 32 / GQ_GROUP;
+      constexpr int MARGIN = SMALLQ ? 8 : 16;
+      constexpr int EVERY = MARGIN / APC;             // chunks between two checks
+      auto check = [&](int chunks_done) {
+        if (chunks_done % EVERY == 0) {
+          __syncwarp();
+          if (__any_sync(0xffffffffu, st.fuller_than(p.q_cap - MARGIN))) st.flush();          // room for the next appends
+          else if (LGX_GQ_DRAIN > 0 && __any_sync(0xffffffffu, st.pending_at_least(LGX_GQ_LOW))) st.drain(LGX_GQ_DRAIN);
+        }
+      };
       gq_chunk<KMAX, SHARE>(va, gid_base, st, th);
       LGX_TMEM_LD32(va, taddr + 96);
       LGX_TMEM_WAIT(va);
@@ -721,15 +911,27 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       // ONE arrival per warp: 256 per-thread arrivals are 256 serialised shared-memory atomics on the path that
       // hands the accumulator buffer back to the MMA warp (the round trip that bounds this kernel)
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);      // the whole tile half is in registers
+      PROF_T(e2);
+      PROF_ADD(1, e2 - e1);
+      TRACE(4 + hw_warp, it, 2, e2);
+      check(1);
       LGX_KEEP(vb);
       LGX_KEEP(vc);
-      gq_chunk<KMAX, SHARE>(vb, gid_base + 4, st, th);
-      if (SMALLQ) { __syncwarp(); if (__any_sync(0xffffffffu, st.fuller_than(p.q_cap - 8))) st.flush(); }
-      gq_chunk<KMAX, SHARE>(vc, gid_base + 8, st, th);
-      gq_chunk<KMAX, SHARE>(va, gid_base + 12, st, th);
-      __syncwarp();
-      if (__any_sync(0xffffffffu, st.fuller_than(p.q_cap - (SMALLQ ? 8 : 16)))) st.flush();
+      gq_chunk<KMAX, SHARE>(vb, gid_base + 1 * APC, st, th);
+      check(2);
+      gq_chunk<KMAX, SHARE>(vc, gid_base + 2 * APC, st, th);
+      check(3);
+      gq_chunk<KMAX, SHARE>(va, gid_base + 3 * APC, st, th);
+      check(4);
+      PROF_T(e3);
+      PROF_ADD(2, e3 - e2);
+      TRACE(4 + hw_warp, it, 3, e3);
     }
+#ifdef LGX_GQ_PROF
+    if (lane == 0) {      // one lane of every epilogue warp: divide by 8 x tiles
+      atomicAdd(&gq_prof[8], prof_acc[0]); atomicAdd(&gq_prof[9], prof_acc[1]); atomicAdd(&gq_prof[10], prof_acc[2]);
+    }
+#endif
     st.flush();
     // stage the register lists, merge the two halves of every row and publish the split's K best groups
 #pragma unroll
@@ -754,6 +956,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();           // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -862,16 +1065,17 @@ __device__ __forceinline__ void rs_drop_masked(const GqRescoreParams& rp, int64_
 // unchanged.  D[row][2t], D[row][2t+1] = scores of items 2t, 2t+1 of the group in every lane of every quad.
 __device__ __forceinline__ void rs_process(const GqRescoreParams& rp, const int32_t* glist, int cnt, const uint4* us,
                                            int64_t uid, float T_lo, RsRow& row, int lane) {
+  constexpr int GPS = 8 / GQ_GROUP;         // groups per MMA slot (the 8 items of one n = 8 B operand)
   const int g = lane >> 2, t = lane & 3;
   const int kb32 = rp.ktot >> 5;            // even: ktot is a multiple of 64
-  for (int m = 0; m < cnt; m += 4) {        // four groups per pass
+  for (int m = 0; m < cnt; m += 4 * GPS) {  // four slots per pass
     const uint4* pr[4];
-    int32_t gid[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      gid[q] = glist[m + q < cnt ? m + q : m];
+      const int gi = m + q * GPS + g / GQ_GROUP;
+      const int32_t gid = glist[gi < cnt ? gi : m];
       // rows past the end of the catalogue are clamped for the load and dropped in rs_push
-      const int64_t j = min((int64_t)gid[q] * GQ_GROUP + g, (int64_t)rp.M - 1);
+      const int64_t j = min((int64_t)gid * GQ_GROUP + (g % GQ_GROUP), (int64_t)rp.M - 1);
       pr[q] = reinterpret_cast<const uint4*>(rp.I_op + j * rp.ktot) + t;
     }
     float c[4][4];
@@ -893,12 +1097,12 @@ __device__ __forceinline__ void rs_process(const GqRescoreParams& rp, const int3
         }
       }
     }
-    // quad g < 4 publishes group g: its lane t holds items 2t and 2t+1
+    // quad g < 4 publishes slot g: its lane t holds the slot's items 2t and 2t+1
     const float sa = g == 0 ? c[0][0] : (g == 1 ? c[1][0] : (g == 2 ? c[2][0] : c[3][0]));
     const float sb = g == 0 ? c[0][1] : (g == 1 ? c[1][1] : (g == 2 ? c[2][1] : c[3][1]));
-    const int32_t gg = g == 0 ? gid[0] : (g == 1 ? gid[1] : (g == 2 ? gid[2] : gid[3]));
-    const bool ok = g < 4 && m + g < cnt;
-    const int64_t j0 = (int64_t)gg * GQ_GROUP + 2 * t;
+    const int gi = m + g * GPS + (2 * t) / GQ_GROUP;
+    const bool ok = g < 4 && gi < cnt;
+    const int64_t j0 = (int64_t)glist[ok ? gi : m] * GQ_GROUP + (2 * t) % GQ_GROUP;
     rs_push(rp, sa, j0, ok, T_lo, row, lane);
     rs_push(rp, sb, j0 + 1, ok, T_lo, row, lane);
     __syncwarp();
@@ -1045,6 +1249,7 @@ GqConfig gq_config(int d, int K, int mode) {
 
 // per-unit overhead of a (user tile, item split) unit in item tiles of 256, for the wave-aware split planner
 constexpr double kGqUnitOverheadTiles = 14.0;
+constexpr int kGqCluster = 2;           // default CTAs per cluster (LGX_SCORE_CLUSTER = 1 / 2 / 4)
 ScorePlan gq_plan(int B, int M, int sms) {
   // both knobs are re-read on every call (experiments sweep them inside one process)
   const char* es = std::getenv("LGX_SCORE_SPLITS");
@@ -1070,7 +1275,19 @@ static int gq_launch2(dim3 grid, const GqConfig& cfg, const CUtensorMap& tm_u, c
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM_LIMIT));
     if (dev < kMaxDevices) configured[dev] = true;
   }
-  k_score_topk_gq<KMAX, SMALLQ, SHARE><<<grid, GQ_THREADS, cfg.smem, st>>>(tm_u, tm_i, p);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = dim3(GQ_THREADS);
+  lc.dynamicSmemBytes = cfg.smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = p.cl > 1 ? 1 : 0;
+  LGX_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_score_topk_gq<KMAX, SMALLQ, SHARE>, tm_u, tm_i, p));
   LGX_CHECK_LAUNCH();
   return LGX_OK;
 }
@@ -1095,18 +1312,22 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
   CUtensorMap tm_u, tm_i;
   int rc = make_operand_map(&tm_u, U_op, B, ktot, GQ_TILE_U);
   if (rc != LGX_OK) return rc;
-  rc = make_operand_map(&tm_i, I_op, M, ktot, GQ_TILE_I);
+  GqParams p;
+  {
+    const char* e = std::getenv("LGX_GQ_DEBUG");
+    p.dbg = e ? std::atoi(e) : 0;
+    // CTAs per cluster sharing the B stream (re-read per call: experiments sweep it inside one process)
+    const char* ec = std::getenv("LGX_SCORE_CLUSTER");
+    const int cl = ec ? std::atoi(ec) : kGqCluster;
+    p.cl = (cl == 2 || cl == 4) ? cl : 1;
+  }
+  rc = make_operand_map(&tm_i, I_op, M, ktot, (p.cl > 1 && !(p.dbg & 128)) ? GQ_TILE_I / p.cl : GQ_TILE_I);
   if (rc != LGX_OK) return rc;
   const ScorePlan plan = gq_plan(B, M, sm_count());
-  GqParams p;
   p.B = B; p.M = M; p.K = K; p.k_blocks = cfg.k_blocks; p.stages = cfg.stages; p.q_cap = cfg.q_cap;
   p.union_bound = cfg.union_bound;
   p.n_splits = plan.n_splits; p.tiles_per_split = plan.tiles_per_split; p.item_offset = item_offset;
   p.mask = make_mask(g); p.users = users;
-  {
-    const char* e = std::getenv("LGX_GQ_DEBUG");
-    p.dbg = e ? std::atoi(e) : 0;
-  }
   p.has_mask = (g != nullptr && !(p.dbg & 4)) ? 1 : 0;
   p.ws_val = reinterpret_cast<float*>(workspace);
   p.ws_idx = reinterpret_cast<int32_t*>(p.ws_val + (size_t)plan.n_splits * B * K);
@@ -1161,7 +1382,7 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
     LGX_CHECK_LAUNCH();
     p.mk_region = bp.region; p.mk_ptr = bp.ptr; p.mk_entries = bp.entries;
   }
-  dim3 grid(plan.n_user_tiles, plan.n_splits);
+  dim3 grid((plan.n_user_tiles + p.cl - 1) / p.cl * p.cl, plan.n_splits);    // whole clusters: padding CTAs are not `live`
   const bool smallq = cfg.q_cap < 32;
   if (K <= 20 && !smallq) rc = gq_launch<20, false>(grid, cfg, tm_u, tm_i, p, st);
   else if (K <= 20) rc = gq_launch<20, true>(grid, cfg, tm_u, tm_i, p, st);
@@ -1179,5 +1400,17 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
   LGX_CHECK_LAUNCH();
   return LGX_OK;
 }
+
+#ifdef LGX_GQ_PROF
+extern "C" __attribute__((visibility("default"))) int lgx_debug_gq_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, gq_trace, sizeof(long long) * 12 * 64 * 6) == cudaSuccess ? 0 : -1;
+}
+extern "C" __attribute__((visibility("default"))) int lgx_debug_gq_prof(unsigned long long* out, int reset) {
+  unsigned long long z[32] = {};
+  if (cudaMemcpyFromSymbol(out, gq_prof, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(gq_prof, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 }  // namespace lgx
