@@ -114,6 +114,12 @@ struct lgx_graph {
   mutable float* hot_val = nullptr;
   mutable lgx::WorkItem* hot_work = nullptr;
   mutable int32_t hot_h = 0;
+  // Train mask of the identity batch (users == NULL: batch row u is user u) bucketed by (user tile, item tile) for
+  // the tcgen05 scoring kernel -- like the reference's allPos (PT/dataloader.py builds it once per dataset), it
+  // depends on the interactions only, so it is built by the first scoring call that needs it and kept.
+  mutable void* mk_cache = nullptr;
+  mutable int64_t mk_key[3] = {-1, -1, -1};      // B, M, item_offset it was built for
+  mutable void* mk_ready = nullptr;              // cudaEvent_t recorded behind the build
 };
 namespace lgx {
 constexpr int kHotMax = 3072;                                           // 192 KB of fp32 rows at d = 16

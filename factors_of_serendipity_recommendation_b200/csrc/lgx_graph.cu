@@ -206,6 +206,8 @@ static void free_graph(lgx_graph* g) {
   cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->values); cudaFree(g->degree);
   cudaFree(g->dinv); cudaFree(g->row_order); cudaFree(g->work); cudaFree(g->long_rows); cudaFree(g->tpos);
   cudaFree(g->hot_ids); cudaFree(g->hot_idx); cudaFree(g->hot_val); cudaFree(g->hot_work);
+  cudaFree(g->mk_cache);
+  if (g->mk_ready) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(g->mk_ready));
   delete g;
 }
 

@@ -34,6 +34,7 @@
 #include "lgx_common.cuh"
 #include "lgx_score_plan.cuh"
 #include "lgx_topk.cuh"
+#include <mutex>
 #include "lgx_tc_ptx.cuh"
 
 namespace lgx {
@@ -52,6 +53,9 @@ constexpr int GQ_MAX_STAGES = 6;
 constexpr int GQ_TMEM_BUF = 256;
 #ifndef LGX_GQ_GROUP
 #define LGX_GQ_GROUP 8
+#endif
+#ifndef LGX_GQ_EARLY_CHUNK
+#define LGX_GQ_EARLY_CHUNK 0
 #endif
 #ifndef LGX_GQ_DRAIN
 #define LGX_GQ_DRAIN 2         // queue entries inserted per lane per check once a lane holds LGX_GQ_LOW (0: only full flushes)
@@ -224,6 +228,17 @@ k_mask_buckets(const GqBucketParams bp) {
     const int c = __ldg(bp.mask.indices + e) - bias;
     out[atomicAdd(&s_cnt[c >> 8], 1)] = (uint16_t)((row << 8) | (c & 255));
   }
+}
+
+// rank of `key` among the set bits of an N x 32-bit map (bits below it)
+template <int N>
+__device__ __forceinline__ int gq_bits_rank(const unsigned (&m)[N], int key) {
+  const int kw = key >> 5;
+  const unsigned low = (1u << (key & 31)) - 1u;
+  int r = 0;
+#pragma unroll
+  for (int w = 0; w < N; ++w) r += w < kw ? __popc(m[w]) : (w == kw ? __popc(m[w] & low) : 0);
+  return r;
 }
 
 // Fallback cursor (a user tile whose entries did not fit the bucket area): one dependent load per train item.
@@ -660,7 +675,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
 #endif
       // what this lane wrote into buffer b the last time (shared-memory addresses, 0 = nothing), or the whole
       // buffer was written by a multi-pass round and is cleared wholesale
-      uint32_t uA0 = 0, uB0 = 0, uA1 = 0, uB1 = 0;
+      uint32_t uA0 = 0, uB0 = 0, uA1 = 0, uB1 = 0;     // first entry a lane wrote
+      uint32_t uC0 = 0, uD0 = 0, uC1 = 0, uD1 = 0;     // second entry (tiles with 33-64 entries)
       bool wide0 = false, wide1 = false;
       // zero what the previous use of buffer b wrote; then every lane may write again
       auto reclaim = [&](uint32_t b) {
@@ -681,8 +697,10 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         } else {
           const uint32_t a = b ? uA1 : uA0, c = b ? uB1 : uB0;
           if (c) { st_shared_u16(a, 0); st_shared_u16(c, 0); }
+          const uint32_t a2 = b ? uC1 : uC0, c2 = b ? uD1 : uD0;
+          if (c2) { st_shared_u16(a2, 0); st_shared_u16(c2, 0); }
         }
-        if (b) { uA1 = uB1 = 0; wide1 = false; } else { uA0 = uB0 = 0; wide0 = false; }
+        if (b) { uA1 = uB1 = uC1 = uD1 = 0; wide1 = false; } else { uA0 = uB0 = uC0 = uD0 = 0; wide0 = false; }
         __syncwarp();     // a slot changes owner between rounds: all zeroing before any new write
       };
       auto publish = [&](uint32_t b, int n, bool more) {
@@ -712,71 +730,102 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
           if (t - wbase >= 32 || t < wbase) { wbase = t; pw = __ldg(ptrw + min(t + lane, n_tiles)); }
           return __shfl_sync(0xffffffffu, pw, t - wbase);
         };
-        // Three prefetch slots used round-robin by a 3x unrolled tile loop: a slot's entry load is issued two tiles before
-        // its use and never moved between registers (a rotating copy made every iteration wait for its own load).
-        struct Pre { int e0, n; uint32_t ent; };
-        Pre s0{0, 0, 0u}, s1{0, 0, 0u}, s2{0, 0, 0u};
+        // Three prefetch slots used round-robin: a slot's entry load is issued three of this warp's tiles before its
+        // use and never moved between registers (a rotating copy made every iteration wait for its own load).
+        struct Pre { int e0, n; uint32_t ent, ent2; };
+        Pre s0{0, 0, 0u, 0u}, s1{0, 0, 0u, 0u}, s2{0, 0, 0u, 0u};
         auto fetch = [&](Pre& q, int it2) {
-          q.e0 = 0; q.n = 0; q.ent = 0u;
+          q.e0 = 0; q.n = 0; q.ent = 0u; q.ent2 = 0u;
           if (it2 < n_my) {
             const int t = t_begin + it2;
             q.e0 = getptr(t);
             q.n = getptr(t + 1) - q.e0;
             if (lane < q.n) q.ent = __ldg(ents + q.e0 + lane);
+            if (lane + 32 < q.n) q.ent2 = __ldg(ents + q.e0 + 32 + lane);
           }
         };
         const uint32_t b = (uint32_t)bw;              // this warp's tiles all use its own buffer
+        // A slot is a star of the tile's (row, train column) graph: centred on a ROW (the row's -2^100 in A_mask, 1.0 in
+        // B_mask for each of its train columns) or on a COLUMN (1.0 in B_mask, -2^100 in A_mask for each row that
+        // trained on it).  Row stars unless the tile has more than 32 dirty rows and fewer dirty columns: such tiles
+        // hold a popular item (Amazon-Book shape: 2.8 % of the tiles, 46 dirty rows but 17 dirty columns on average)
+        // and cost two builder <-> MMA round trips (~6 000 cycles, ten times per CTA) when ranked by row.
         auto process = [&](const Pre& q) {
           const int n_e = q.n, e0 = q.e0;
-          const uint32_t ent = q.ent;
-          if (n_e <= 32) {
-            const bool valid = lane < n_e;
-            const int row = (int)(ent >> 8), col = (int)(ent & 255u);
-            const unsigned bit = valid ? 1u << (row & 31) : 0u;
-            const int ws = row >> 5;
-            const unsigned m0 = __reduce_or_sync(0xffffffffu, ws == 0 ? bit : 0u);
-            const unsigned m1 = __reduce_or_sync(0xffffffffu, ws == 1 ? bit : 0u);
-            const unsigned m2 = __reduce_or_sync(0xffffffffu, ws == 2 ? bit : 0u);
-            const unsigned m3 = __reduce_or_sync(0xffffffffu, ws == 3 ? bit : 0u);
-            const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), n_dirty = c2 + __popc(m3);
-            const unsigned mw = ws == 0 ? m0 : (ws == 1 ? m1 : (ws == 2 ? m2 : m3));
-            const int rank = (ws == 0 ? 0 : (ws == 1 ? c0 : (ws == 2 ? c1 : c2))) + __popc(mw & ((1u << (row & 31)) - 1u));
+          if (n_e <= 64) {
+            // up to two entries per lane, all in registers
+            const bool v0 = lane < n_e, v1 = lane + 32 < n_e;
+            const int row0 = (int)(q.ent >> 8), col0 = (int)(q.ent & 255u);
+            const int row1 = (int)(q.ent2 >> 8), col1 = (int)(q.ent2 & 255u);
+            unsigned m[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              m[w] = __reduce_or_sync(0xffffffffu, ((v0 && (row0 >> 5) == w) ? 1u << (row0 & 31) : 0u) |
+                                                       ((v1 && (row1 >> 5) == w) ? 1u << (row1 & 31) : 0u));
+            int n_dirty = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+            int rank0 = gq_bits_rank<4>(m, row0), rank1 = gq_bits_rank<4>(m, row1);
+            if (n_dirty > 32) {
+              unsigned cm[8];
+              int n_cols = 0;
+#pragma unroll
+              for (int w = 0; w < 8; ++w) {
+                cm[w] = __reduce_or_sync(0xffffffffu, ((v0 && (col0 >> 5) == w) ? 1u << (col0 & 31) : 0u) |
+                                                          ((v1 && (col1 >> 5) == w) ? 1u << (col1 & 31) : 0u));
+                n_cols += __popc(cm[w]);
+              }
+              if (n_cols < n_dirty) {
+                n_dirty = n_cols;
+                rank0 = gq_bits_rank<8>(cm, col0);
+                rank1 = gq_bits_rank<8>(cm, col1);
+              }
+            }
             const int nrounds = n_dirty > 32 ? (n_dirty + 31) >> 5 : 1;
             for (int r = 0; r < nrounds; ++r) {
               reclaim(b);
-              if (valid && (rank >> 5) == r) {
-                const int slot = 32 * (int)b + (rank & 31);
-                const uint32_t a = sAm + gq_swz(row, slot), c = sBm + gq_swz(col, slot);
-                st_shared_u16(a, GQ_BF16_NEG_BIG);      // several entries of one row write the same value
+              if (v0 && (rank0 >> 5) == r) {
+                const int slot = 32 * (int)b + (rank0 & 31);
+                const uint32_t a = sAm + gq_swz(row0, slot), c = sBm + gq_swz(col0, slot);
+                st_shared_u16(a, GQ_BF16_NEG_BIG);      // entries of one star write the centre's value several times
                 st_shared_u16(c, GQ_BF16_ONE);
                 if (b) { uA1 = a; uB1 = c; } else { uA0 = a; uB0 = c; }
+              }
+              if (v1 && (rank1 >> 5) == r) {
+                const int slot = 32 * (int)b + (rank1 & 31);
+                const uint32_t a = sAm + gq_swz(row1, slot), c = sBm + gq_swz(col1, slot);
+                st_shared_u16(a, GQ_BF16_NEG_BIG);
+                st_shared_u16(c, GQ_BF16_ONE);
+                if (b) { uC1 = a; uD1 = c; } else { uC0 = a; uD0 = c; }
               }
               publish(b, min(32, n_dirty - 32 * r), r + 1 < nrounds);
             }
           } else {
-            // more than 32 train entries in one 128 x 256 tile: pass 1 collects the dirty rows, every round
-            // re-reads the entries it needs; the buffer is cleared wholesale afterwards
-            unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            // more than 64 train entries in one 128 x 256 tile: pass 1 collects the dirty rows and columns, every
+            // round re-reads the entries it needs; the buffer is cleared wholesale afterwards
+            unsigned m[4] = {0u, 0u, 0u, 0u}, cm[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             for (int cbase = 0; cbase < n_e; cbase += 32) {
               const bool valid = cbase + lane < n_e;
               const uint32_t e = valid ? (uint32_t)__ldg(ents + e0 + cbase + lane) : 0u;
-              const int row = (int)(e >> 8), ws = row >> 5;
-              const unsigned bit = valid ? 1u << (row & 31) : 0u;
-              m0 |= __reduce_or_sync(0xffffffffu, ws == 0 ? bit : 0u);
-              m1 |= __reduce_or_sync(0xffffffffu, ws == 1 ? bit : 0u);
-              m2 |= __reduce_or_sync(0xffffffffu, ws == 2 ? bit : 0u);
-              m3 |= __reduce_or_sync(0xffffffffu, ws == 3 ? bit : 0u);
+              const int row = (int)(e >> 8), col = (int)(e & 255u);
+#pragma unroll
+              for (int w = 0; w < 4; ++w)
+                m[w] |= __reduce_or_sync(0xffffffffu, (valid && (row >> 5) == w) ? 1u << (row & 31) : 0u);
+#pragma unroll
+              for (int w = 0; w < 8; ++w)
+                cm[w] |= __reduce_or_sync(0xffffffffu, (valid && (col >> 5) == w) ? 1u << (col & 31) : 0u);
             }
-            const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), n_dirty = c2 + __popc(m3);
+            int n_dirty = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]), n_cols = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) n_cols += __popc(cm[w]);
+            const bool by_col = n_dirty > 32 && n_cols < n_dirty;
+            if (by_col) n_dirty = n_cols;
             const int nrounds = n_dirty > 32 ? (n_dirty + 31) >> 5 : 1;
             for (int r = 0; r < nrounds; ++r) {
               reclaim(b);
               for (int cbase = 0; cbase < n_e; cbase += 32) {
                 if (cbase + lane < n_e) {
                   const uint32_t e = (uint32_t)__ldg(ents + e0 + cbase + lane);
-                  const int row = (int)(e >> 8), col = (int)(e & 255u), ws = row >> 5;
-                  const unsigned mw = ws == 0 ? m0 : (ws == 1 ? m1 : (ws == 2 ? m2 : m3));
-                  const int rank = (ws == 0 ? 0 : (ws == 1 ? c0 : (ws == 2 ? c1 : c2))) + __popc(mw & ((1u << (row & 31)) - 1u));
+                  const int row = (int)(e >> 8), col = (int)(e & 255u);
+                  const int rank = by_col ? gq_bits_rank<8>(cm, col) : gq_bits_rank<4>(m, row);
                   if ((rank >> 5) == r) {
                     const int slot = 32 * (int)b + (rank & 31);
                     st_shared_u16(sAm + gq_swz(row, slot), GQ_BF16_NEG_BIG);
@@ -789,13 +838,25 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
             }
           }
         };
+        // ONE copy of process() (a 3x unrolled loop tripled ~700 instructions of rarely executed code and the warp
+        // ran out of the instruction cache): the slot to use is selected with warp-uniform selects, and the slot just
+        // consumed is refilled by loads straight into its own registers, three of this warp's tiles ahead.
         fetch(s0, bw);
         fetch(s1, bw + 2);
-        for (int it = bw; it < n_my; it += 6) {
-          fetch(s2, it + 4);
-          process(s0);
-          if (it + 2 < n_my) { fetch(s0, it + 6); process(s1); }
-          if (it + 4 < n_my) { fetch(s1, it + 8); process(s2); }
+        fetch(s2, bw + 4);
+        int k = 0;
+#pragma unroll 1
+        for (int it = bw; it < n_my; it += 2) {
+          Pre cur;
+          cur.e0 = k == 0 ? s0.e0 : (k == 1 ? s1.e0 : s2.e0);
+          cur.n = k == 0 ? s0.n : (k == 1 ? s1.n : s2.n);
+          cur.ent = k == 0 ? s0.ent : (k == 1 ? s1.ent : s2.ent);
+          cur.ent2 = k == 0 ? s0.ent2 : (k == 1 ? s1.ent2 : s2.ent2);
+          if (k == 0) fetch(s0, it + 6);
+          else if (k == 1) fetch(s1, it + 6);
+          else fetch(s2, it + 6);
+          k = k == 2 ? 0 : k + 1;
+          process(cur);
         }
       } else if (bw == 0) {
         // ---- fallback: walk the 128 sorted train lists here (4 rows per lane, one dependent load per train item)
@@ -896,6 +957,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       constexpr int APC = 32 / GQ_GROUP;
       constexpr int MARGIN = SMALLQ ? 8 : 16;
       constexpr int EVERY = MARGIN / APC;             // chunks between two checks
+      static_assert(!LGX_GQ_EARLY_CHUNK || EVERY >= 2, "two chunks are processed before the first check");
       auto check = [&](int chunks_done) {
         if (chunks_done % EVERY == 0) {
           __syncwarp();
@@ -905,6 +967,12 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       };
       gq_chunk<KMAX, SHARE>(va, gid_base, st, th);
       LGX_TMEM_LD32(va, taddr + 96);
+#if LGX_GQ_EARLY_CHUNK
+      // the second chunk is processed while the fourth load is in flight (the wait right behind the load exposed
+      // its whole latency once per tile)
+      LGX_KEEP(vb);
+      gq_chunk<KMAX, SHARE>(vb, gid_base + 1 * (32 / GQ_GROUP), st, th);
+#endif
       LGX_TMEM_WAIT(va);
       tc_fence_before();
       __syncwarp();
@@ -915,9 +983,11 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       PROF_ADD(1, e2 - e1);
       TRACE(4 + hw_warp, it, 2, e2);
       check(1);
-      LGX_KEEP(vb);
       LGX_KEEP(vc);
+#if !LGX_GQ_EARLY_CHUNK
+      LGX_KEEP(vb);
       gq_chunk<KMAX, SHARE>(vb, gid_base + 1 * APC, st, th);
+#endif
       check(2);
       gq_chunk<KMAX, SHARE>(vc, gid_base + 2 * APC, st, th);
       check(3);
@@ -1249,7 +1319,7 @@ GqConfig gq_config(int d, int K, int mode) {
 
 // per-unit overhead of a (user tile, item split) unit in item tiles of 256, for the wave-aware split planner
 constexpr double kGqUnitOverheadTiles = 14.0;
-constexpr int kGqCluster = 2;           // default CTAs per cluster (LGX_SCORE_CLUSTER = 1 / 2 / 4)
+constexpr int kGqCluster = 1;           // default CTAs per cluster (LGX_SCORE_CLUSTER = 1 / 2 / 4)
 ScorePlan gq_plan(int B, int M, int sms) {
   // both knobs are re-read on every call (experiments sweep them inside one process)
   const char* es = std::getenv("LGX_SCORE_SPLITS");
@@ -1361,9 +1431,34 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
     const size_t off_ptr = off_region + ((sizeof(int64_t) * plan.n_user_tiles + 255) & ~(size_t)255);
     const size_t off_ent = off_ptr + ((sizeof(int32_t) * (size_t)plan.n_user_tiles * (n_tiles + 1) + 255) & ~(size_t)255);
     const size_t total = off_ent + sizeof(uint16_t) * cap + 256;
-    LGX_CHECK_CUDA(cudaMallocAsync(&mk_scratch, total, st));
-    unsigned char* base = reinterpret_cast<unsigned char*>(mk_scratch);
-    LGX_CHECK_CUDA(cudaMemsetAsync(base, 0, 256, st));
+    // identity batch (users == NULL): the buckets depend on the graph only and are kept with it
+    static const bool cache_on = [] { const char* e = std::getenv("LGX_SCORE_MASK_CACHE"); return !e || std::atoi(e) != 0; }();
+    const bool cacheable = cache_on && users == nullptr;
+    bool cached = false;
+    unsigned char* base = nullptr;
+    static std::mutex mu;                    // held until this call's launches are queued
+    std::unique_lock<std::mutex> lock(mu, std::defer_lock);
+    if (cacheable) {
+      lock.lock();
+      if (g->mk_cache && g->mk_key[0] == B && g->mk_key[1] == M && g->mk_key[2] == item_offset) {
+        cached = true;
+        LGX_CHECK_CUDA(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(g->mk_ready), 0));
+      } else {
+        if (g->mk_cache) { LGX_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(g->mk_cache); g->mk_cache = nullptr; }
+        LGX_CHECK_CUDA(cudaMalloc(&g->mk_cache, total));
+        if (!g->mk_ready) {
+          cudaEvent_t ev;
+          LGX_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          g->mk_ready = ev;
+        }
+        g->mk_key[0] = B; g->mk_key[1] = M; g->mk_key[2] = item_offset;
+      }
+      base = reinterpret_cast<unsigned char*>(g->mk_cache);
+    } else {
+      LGX_CHECK_CUDA(cudaMallocAsync(&mk_scratch, total, st));
+      base = reinterpret_cast<unsigned char*>(mk_scratch);
+    }
+    if (!cached) LGX_CHECK_CUDA(cudaMemsetAsync(base, 0, 256, st));
     GqBucketParams bp;
     bp.mask = p.mask; bp.mask.m_items_hint = g->m_items; bp.users = users; bp.B = B; bp.M = M; bp.n_tiles = n_tiles; bp.item_offset = item_offset;
     bp.cursor = reinterpret_cast<unsigned long long*>(base);
@@ -1378,8 +1473,11 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
         if (dev < kMaxDevices) configured[dev] = 200 * 1024;
       }
     }
-    k_mask_buckets<<<plan.n_user_tiles, MB_THREADS, bucket_smem, st>>>(bp);
-    LGX_CHECK_LAUNCH();
+    if (!cached) {
+      k_mask_buckets<<<plan.n_user_tiles, MB_THREADS, bucket_smem, st>>>(bp);
+      LGX_CHECK_LAUNCH();
+      if (cacheable) LGX_CHECK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(g->mk_ready), st));
+    }
     p.mk_region = bp.region; p.mk_ptr = bp.ptr; p.mk_entries = bp.entries;
   }
   dim3 grid((plan.n_user_tiles + p.cl - 1) / p.cl * p.cl, plan.n_splits);    // whole clusters: padding CTAs are not `live`
