@@ -57,6 +57,12 @@ constexpr int GQ_TMEM_BUF = 256;
 #ifndef LGX_GQ_EARLY_CHUNK
 #define LGX_GQ_EARLY_CHUNK 0
 #endif
+#ifndef LGX_GQ_EVERY
+#define LGX_GQ_EVERY 2
+#endif
+#ifndef LGX_GQ_SMALLQ_BELOW
+#define LGX_GQ_SMALLQ_BELOW 32      // 24: one check per tile for 24-row queues measured 15 % slower (fewer, longer drains)
+#endif
 #ifndef LGX_GQ_DRAIN
 #define LGX_GQ_DRAIN 2         // queue entries inserted per lane per check once a lane holds LGX_GQ_LOW (0: only full flushes)
 #endif
@@ -77,6 +83,7 @@ struct GqParams {
   int q_cap;
   int union_bound;
   int n_splits, tiles_per_split;
+  int rotate;             // 1: every CTA starts its item-tile walk at its own offset
   int cl;                 // CTAs per cluster sharing every B tile by TMA multicast (1 = no cluster)
   int has_mask;
   int dbg;                // LGX_GQ_DEBUG (experiments): 1 = TMEM loads only, 2 = no TMEM loads either, 4 = no mask,
@@ -388,6 +395,9 @@ __device__ unsigned long long gq_prof[32];
 // timeline of one CTA (blockIdx.x == 7), tiles [GQ_TR0, GQ_TR0 + 64): [role 0..11][tile][event 0..5] = clock64
 constexpr int GQ_TR0 = 120;
 __device__ long long gq_trace[12 * 64 * 6];
+// per CTA (blockIdx.x < 1024): smid, globaltimer at kernel entry / MMA loop start / MMA loop end / last epilogue warp done / exit
+__device__ long long gq_cta[1024 * 8];
+__device__ __forceinline__ long long gq_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define PROF_T(x) const long long x = clock64()
 #define PROF_ADD(i, v) (prof_acc[i] += (unsigned long long)(v))
 #define TRACE(role, it, ev, t)                                                                     \
@@ -443,6 +453,13 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   const int n_tiles = (p.M + GQ_TILE_I - 1) / GQ_TILE_I;
   const int t_begin = split * p.tiles_per_split;
   const int n_my = max(0, min(n_tiles, t_begin + p.tiles_per_split) - t_begin);
+  // Every CTA walks its item tiles from a different starting point (and wraps): the CTAs of a wave start together
+  // and otherwise ask the L2 for the same B tile at the same moment, tile after tile.  The list-walking mask
+  // fallback needs ascending tiles, so a user tile without pre-bucketed entries keeps the plain order.
+  int rot = 0;
+  if (p.rotate && n_my > 1 && !(p.has_mask && (p.mk_region == nullptr || p.mk_region[min(u_tile, (p.B - 1) / GQ_TILE_U)] < 0)))
+    rot = (int)(((long long)u_tile * 40503LL) % n_my);
+  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_my ? t - n_my : t); };
   // Cluster mode (p.cl = 2 or 4 CTAs along x: neighbouring user tiles, the same item tiles): CTA r loads rows
   // [r, r + 1) * 256 / cl of every B tile and TMA multicasts them into all cl CTAs, so a tile leaves the L2 once per
   // cluster instead of once per CTA -- the B stream out of the L2 (32 KB per 512 tensor cycles per SM) is what the
@@ -457,6 +474,13 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
 #ifdef LGX_GQ_PROF
   unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long pstart = clock64();
+  if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    gq_cta[blockIdx.x * 8 + 0] = smid;
+    gq_cta[blockIdx.x * 8 + 1] = gq_gtime();
+    gq_cta[blockIdx.x * 8 + 6] = clock64();
+  }
 #endif
 
   if (warp == 0 && lane == 0) {
@@ -510,7 +534,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_my; ++it) {
-        const int row0 = (t_begin + it) * GQ_TILE_I;
+        const int row0 = tile_of(it) * GQ_TILE_I;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           PROF_T(tw0);
           mbar_wait<false>(bar_empty + 8 * stage, phase ^ 1);
@@ -646,6 +670,9 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         return v_next;
       };
       PROF_T(mstart);
+#ifdef LGX_GQ_PROF
+      if (lane == 0 && blockIdx.y == 0 && blockIdx.x < 1024) gq_cta[blockIdx.x * 8 + 2] = gq_gtime();
+#endif
       int v = pipelined ? ready(0, 0, 0, 0u) : 0;
       for (int it = 0; it < n_my; it += 2) {
         v = tile(it, 0, v);
@@ -653,6 +680,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       }
 #ifdef LGX_GQ_PROF
       PROF_T(mend);
+      if (lane == 0 && blockIdx.y == 0 && blockIdx.x < 1024) gq_cta[blockIdx.x * 8 + 3] = gq_gtime();
       if (lane == 0) {
         atomicAdd(&gq_prof[0], prof_acc[0]); atomicAdd(&gq_prof[1], (unsigned long long)(mend - mstart)); atomicAdd(&gq_prof[2], prof_acc[2]);
         atomicAdd(&gq_prof[3], prof_acc[3]); atomicAdd(&gq_prof[4], prof_acc[4]); atomicAdd(&gq_prof[5], prof_acc[5]);
@@ -737,7 +765,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         auto fetch = [&](Pre& q, int it2) {
           q.e0 = 0; q.n = 0; q.ent = 0u; q.ent2 = 0u;
           if (it2 < n_my) {
-            const int t = t_begin + it2;
+            const int t = tile_of(it2);
             q.e0 = getptr(t);
             q.n = getptr(t + 1) - q.e0;
             if (lane < q.n) q.ent = __ldg(ents + q.e0 + lane);
@@ -932,7 +960,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       PROF_ADD(0, e1 - e0);
       TRACE(4 + hw_warp, it, 0, e0); TRACE(4 + hw_warp, it, 1, e1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GQ_TMEM_BUF + h * 128);
-      const int gid_base = ((t_begin + it) * GQ_TILE_I + h * 128) / GQ_GROUP;
+      const int gid_base = (tile_of(it) * GQ_TILE_I + h * 128) / GQ_GROUP;
       if (p.dbg & 2) {                        // experiment: barrier handshake only (TMA / MMA / builder floor)
         tc_fence_before();
         __syncwarp();
@@ -953,16 +981,19 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       LGX_KEEP(vb);
       LGX_KEEP(vc);
       // flush checks: a lane appends at most APC = 32 / GQ_GROUP candidates per chunk; small queues are checked with
-      // a margin of 8 appends, deep ones with a margin of 16
+      // a margin of 8 appends (every 2 chunks at 8-column groups), deep ones once per tile with a margin of 16
       constexpr int APC = 32 / GQ_GROUP;
-      constexpr int MARGIN = SMALLQ ? 8 : 16;
-      constexpr int EVERY = MARGIN / APC;             // chunks between two checks
+      constexpr int EVERY = SMALLQ ? LGX_GQ_EVERY : 4;   // chunks between two checks
+      constexpr int MARGIN = EVERY * APC;
       static_assert(!LGX_GQ_EARLY_CHUNK || EVERY >= 2, "two chunks are processed before the first check");
       auto check = [&](int chunks_done) {
         if (chunks_done % EVERY == 0) {
           __syncwarp();
-          if (__any_sync(0xffffffffu, st.fuller_than(p.q_cap - MARGIN))) st.flush();          // room for the next appends
-          else if (LGX_GQ_DRAIN > 0 && __any_sync(0xffffffffu, st.pending_at_least(LGX_GQ_LOW))) st.drain(LGX_GQ_DRAIN);
+          // one insertion loop per check site (the drain loop, unbounded when a queue needs room for the next
+          // appends): every jump over an inlined loop body costs an instruction-fetch bubble on the common path
+          const bool room = __any_sync(0xffffffffu, st.fuller_than(p.q_cap - MARGIN));
+          if (room || (LGX_GQ_DRAIN > 0 && __any_sync(0xffffffffu, st.pending_at_least(LGX_GQ_LOW))))
+            st.drain(room ? (1 << 20) : LGX_GQ_DRAIN);
         }
       };
       gq_chunk<KMAX, SHARE>(va, gid_base, st, th);
@@ -998,6 +1029,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       TRACE(4 + hw_warp, it, 3, e3);
     }
 #ifdef LGX_GQ_PROF
+    if (lane == 0 && hw_warp == 0 && blockIdx.y == 0 && blockIdx.x < 1024) gq_cta[blockIdx.x * 8 + 4] = gq_gtime();
     if (lane == 0) {      // one lane of every epilogue warp: divide by 8 x tiles
       atomicAdd(&gq_prof[8], prof_acc[0]); atomicAdd(&gq_prof[9], prof_acc[1]); atomicAdd(&gq_prof[10], prof_acc[2]);
     }
@@ -1027,6 +1059,12 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (mc) cluster_sync_all();           // no CTA leaves while a peer may still multicast into it or signal its barriers
+#ifdef LGX_GQ_PROF
+  if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {
+    gq_cta[blockIdx.x * 8 + 5] = gq_gtime();
+    gq_cta[blockIdx.x * 8 + 7] = clock64();
+  }
+#endif
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1390,6 +1428,8 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
     const char* ec = std::getenv("LGX_SCORE_CLUSTER");
     const int cl = ec ? std::atoi(ec) : kGqCluster;
     p.cl = (cl == 2 || cl == 4) ? cl : 1;
+    const char* er = std::getenv("LGX_SCORE_ROTATE");
+    p.rotate = er ? std::atoi(er) : 0;      // measured: 3 % faster without mask / epilogue work, 2 % slower with
   }
   rc = make_operand_map(&tm_i, I_op, M, ktot, (p.cl > 1 && !(p.dbg & 128)) ? GQ_TILE_I / p.cl : GQ_TILE_I);
   if (rc != LGX_OK) return rc;
@@ -1481,7 +1521,7 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
     p.mk_region = bp.region; p.mk_ptr = bp.ptr; p.mk_entries = bp.entries;
   }
   dim3 grid((plan.n_user_tiles + p.cl - 1) / p.cl * p.cl, plan.n_splits);    // whole clusters: padding CTAs are not `live`
-  const bool smallq = cfg.q_cap < 32;
+  const bool smallq = cfg.q_cap < LGX_GQ_SMALLQ_BELOW;     // deep queues: one check per tile with a 16-append margin
   if (K <= 20 && !smallq) rc = gq_launch<20, false>(grid, cfg, tm_u, tm_i, p, st);
   else if (K <= 20) rc = gq_launch<20, true>(grid, cfg, tm_u, tm_i, p, st);
   else if (K <= 24 && !smallq) rc = gq_launch<24, false>(grid, cfg, tm_u, tm_i, p, st);
@@ -1500,6 +1540,9 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
 }
 
 #ifdef LGX_GQ_PROF
+extern "C" __attribute__((visibility("default"))) int lgx_debug_gq_cta(long long* out) {
+  return cudaMemcpyFromSymbol(out, gq_cta, sizeof(long long) * 1024 * 8) == cudaSuccess ? 0 : -1;
+}
 extern "C" __attribute__((visibility("default"))) int lgx_debug_gq_trace(long long* out) {
   return cudaMemcpyFromSymbol(out, gq_trace, sizeof(long long) * 12 * 64 * 6) == cudaSuccess ? 0 : -1;
 }
