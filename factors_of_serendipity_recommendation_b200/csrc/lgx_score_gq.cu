@@ -57,6 +57,12 @@ constexpr int GQ_TMEM_BUF = 256;
 #ifndef LGX_GQ_EARLY_CHUNK
 #define LGX_GQ_EARLY_CHUNK 0
 #endif
+#ifndef LGX_GQ_READY_AFTER
+#define LGX_GQ_READY_AFTER 3   // the next tile's readiness checks run behind this many queued MMAs of the last K block
+#endif
+#ifndef LGX_GQ_TH_REFRESH
+#define LGX_GQ_TH_REFRESH 0
+#endif
 #ifndef LGX_GQ_EVERY
 #define LGX_GQ_EVERY 2
 #endif
@@ -645,7 +651,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
           const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (GQ_STAGE >> 4));
           if (elect_one()) {
             tc_mma_f16(tmem_d, adesc, bdesc, GQ_IDESC, acc);
-            tc_mma_f16(tmem_d, adesc + 2, bdesc + 2, GQ_IDESC, 1u);
+            if (LGX_GQ_READY_AFTER >= 2) tc_mma_f16(tmem_d, adesc + 2, bdesc + 2, GQ_IDESC, 1u);
+            if (LGX_GQ_READY_AFTER >= 3) tc_mma_f16(tmem_d, adesc + 4, bdesc + 4, GQ_IDESC, 1u);
           }
           __syncwarp();
           int nstage = stage + 1;
@@ -653,7 +660,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
           if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
           if (pipelined && last && it + 1 < n_my) v_next = ready(it + 1, buf ^ 1, nstage, nphase);
           if (elect_one()) {
-            tc_mma_f16(tmem_d, adesc + 4, bdesc + 4, GQ_IDESC, 1u);
+            if (LGX_GQ_READY_AFTER < 2) tc_mma_f16(tmem_d, adesc + 2, bdesc + 2, GQ_IDESC, 1u);
+            if (LGX_GQ_READY_AFTER < 3) tc_mma_f16(tmem_d, adesc + 4, bdesc + 4, GQ_IDESC, 1u);
             tc_mma_f16(tmem_d, adesc + 6, bdesc + 6, GQ_IDESC, 1u);
             if (mc) tc_commit_mc(bar_empty + 8 * stage, mc_mask);
             else tc_commit(bar_empty + 8 * stage);
@@ -967,7 +975,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         continue;
       }
-      const float th = (p.dbg & 1) ? CUDART_INF_F : st.filter();   // experiment 1: loads + max tree, nothing appended
+      float th = (p.dbg & 1) ? CUDART_INF_F : st.filter();   // experiment 1: loads + max tree, nothing appended
       // Three register buffers: the loads of the first three chunks are issued back to back and the fourth as soon as
       // the first chunk is consumed, so the TMEM buffer goes back to the MMA warp after ONE chunk of epilogue work
       // instead of three.  The accumulator round trip (epilogue hold time + MMA latency) over two TMEM buffers is what
@@ -992,8 +1000,10 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
           // one insertion loop per check site (the drain loop, unbounded when a queue needs room for the next
           // appends): every jump over an inlined loop body costs an instruction-fetch bubble on the common path
           const bool room = __any_sync(0xffffffffu, st.fuller_than(p.q_cap - MARGIN));
-          if (room || (LGX_GQ_DRAIN > 0 && __any_sync(0xffffffffu, st.pending_at_least(LGX_GQ_LOW))))
+          if (room || (LGX_GQ_DRAIN > 0 && __any_sync(0xffffffffu, st.pending_at_least(LGX_GQ_LOW)))) {
             st.drain(room ? (1 << 20) : LGX_GQ_DRAIN);
+            if (LGX_GQ_TH_REFRESH && !(p.dbg & 1)) th = st.filter();     // the rest of the tile filters with the new bound
+          }
         }
       };
       gq_chunk<KMAX, SHARE>(va, gid_base, st, th);
@@ -1090,7 +1100,7 @@ struct GqRescoreParams {
 
 constexpr int RS_WARPS = 8;
 #ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 4          // latency-bound (dependent global loads per row): 32 resident warps per SM
+#define RS_MIN_BLOCKS 3          // 85 registers, no spills (4 blocks = 64 registers spilled 72 bytes per thread; same speed)
 #endif
 constexpr int RS_CAP = 160;      // candidate buffer per warp: compressed to the best K whenever > RS_CAP - 64 are held
 constexpr int RS_KMAX = 32;
