@@ -285,6 +285,8 @@ struct GqEpi {
   int32_t li[KMAX];
   uint32_t qb;            // shared-memory address of this thread's queue slot 0; slot n at qb + n * ROWB
   int qn, qh;             // queue slots [qh, qn) hold candidates not yet inserted (FIFO; both reset when it empties)
+  unsigned pubs;          // bounded drains since the start (SHARE: throttles the global bound exchange)
+  float gseen;            // SHARE: best row bound read from the other splits so far
   static constexpr uint32_t ROWB = GQ_EPI * 8;
   float* thr_mine; const float* thr_other;
   float4* quart_mine; const float4* quart_other;
@@ -302,6 +304,8 @@ struct GqEpi {
       li[p] = INT32_MAX;
     }
     tu = -CUDART_INF_F;
+    pubs = 0u;
+    gseen = -CUDART_INF_F;
   }
   // One 8-byte store per candidate at an address derived from the COUNT: the store's address register is never
   // overwritten (a pointer bumped after every store made each predicated bump wait for the store to read it).
@@ -334,7 +338,7 @@ struct GqEpi {
   __device__ __forceinline__ void flush() {
     while (qh < qn) pop_insert();
     qh = qn = 0;
-    publish();
+    publish(true);
   }
   // at most `iters` candidates per lane: one lane's long queue no longer makes its warp (and through the accumulator
   // hand-back, the whole pipeline) wait for a 16-deep insertion burst
@@ -344,10 +348,14 @@ struct GqEpi {
       if (!__any_sync(0xffffffffu, qh < qn)) break;
     }
     if (qh == qn) qh = qn = 0;
-    publish();
+    publish(iters > LGX_GQ_DRAIN);
   }
-  __device__ __forceinline__ void publish() {
-    const unsigned gb = (SHARE && gbound) ? *reinterpret_cast<const volatile unsigned*>(gbound) : 0u;
+  // `global`: also exchange the row bound with the other item splits of this row (SHARE).  That is a global load and
+  // an atomic, ~1 000 cycles of latency in the middle of a drain: done on full flushes and on every 8th bounded drain
+  // only (with it on every drain a split unit cost as much as ~80 item tiles of scoring).
+  __device__ __forceinline__ void publish(bool global) {
+    const bool glob = SHARE && gbound && (global || (++pubs & 7u) == 0u);
+    const unsigned gb = glob ? *reinterpret_cast<const volatile unsigned*>(gbound) : 0u;
     float t = lv[KMAX - 1];
     if (use_union) {
       const float a1 = lv[KMAX / 4 - 1], a2 = lv[KMAX / 2 - 1], a3 = lv[3 * KMAX / 4 - 1];
@@ -356,11 +364,12 @@ struct GqEpi {
       *quart_mine = make_float4(a1, a2, a3, t);
       t = fmaxf(max3(fminf(a1, b3), fminf(a2, b2), fminf(a3, b1)), fmaxf(t, b4));
     }
-    if (SHARE && gbound) {
+    if (glob) {
       const unsigned mine = (t != t) ? 0u : gq_ord_encode(t);
       if (mine > gb) atomicMax(gbound, mine);
-      t = fmaxf(t, gq_ord_decode(gb));
+      gseen = fmaxf(gseen, gq_ord_decode(gb));
     }
+    if (SHARE) t = fmaxf(t, gseen);          // the last bound seen from the other splits stays valid
     const int tb = __float_as_int(t);                  // publish prev_float(bound); -inf stays -inf
     tu = (t == -CUDART_INF_F || t != t) ? -CUDART_INF_F
                                        : __int_as_float(tb > 0 ? tb - 1 : (tb == 0 ? (int)0x80000001 : tb + 1));
@@ -1366,7 +1375,11 @@ GqConfig gq_config(int d, int K, int mode) {
 }
 
 // per-unit overhead of a (user tile, item split) unit in item tiles of 256, for the wave-aware split planner
-constexpr double kGqUnitOverheadTiles = 14.0;
+// Re-fitted for the round-2 kernel (profiles/r2_score_split_sweep.txt): a tile now costs half of what it did, a unit's
+// start-up (cold thresholds: every group is a candidate until the lists fill) does not, so the same overhead is worth
+// 45 - 180 tiles; Amazon-Book catalogue, 103 user tiles: 1 split 0.381 ms, 4 splits 0.460 ms; 52 tiles: 2 splits
+// 0.263 ms, 5 splits 0.293 ms; 32 tiles: 4 splits 0.210 ms.
+constexpr double kGqUnitOverheadTiles = 60.0;
 constexpr int kGqCluster = 1;           // default CTAs per cluster (LGX_SCORE_CLUSTER = 1 / 2 / 4)
 ScorePlan gq_plan(int B, int M, int sms) {
   // both knobs are re-read on every call (experiments sweep them inside one process)
