@@ -7,23 +7,27 @@
 // 5 issue slots per score, ~85 % of them outside the max filter: per-column candidate appends (a warp holds 32
 // independent rows, so "rare per row" is "always" per warp), the train-mask sweep and the mask cursor's dependent
 // global loads.  Here
-//   * the TRAIN MASK IS APPLIED BY THE TENSOR CORE: two helper warps walk the 128 rows' sorted train lists and, per
-//     item tile, give every row that has train items in the tile one K-slot of a small mask operand pair in shared
-//     memory: A_mask[row, slot] = -2^100, B_mask[col, slot] = 1 for the row's train columns.  One or two extra
+//   * the TRAIN MASK IS APPLIED BY THE TENSOR CORE: two helper warps take the tile's pre-bucketed train entries
+//     (k_mask_buckets) and give every row that has train items in the tile one K-slot of a small mask operand pair in
+//     shared memory: A_mask[row, slot] = -2^100, B_mask[col, slot] = 1 for the row's train columns (or one slot per
+//     COLUMN when the tile holds a popular item: more than 32 dirty rows, fewer dirty columns).  One or two extra
 //     K = 16 MMA steps add -2^100 to exactly the train (row, col) scores, so the epilogue has no mask code at all;
 //   * the epilogue keeps the top-K GROUPS of 8 columns by group maximum (the 3-input max tree it needs anyway):
 //     a candidate is one predicated (max, group id) append per group instead of an 8-column scan.  The K-th best
 //     group maximum is a valid lower bound on the row's K-th best score (K distinct items score at least that),
-//     so every item of the final top-K lies in one of the K kept groups;
+//     so every item of the final top-K lies in one of the K kept groups.  Queued candidates are inserted into the
+//     register-resident sorted list at most two per lane per check (every two 32-column chunks): one lane's long
+//     queue must not make its warp -- and through the accumulator hand-back the whole pipeline -- wait;
 //   * a second small kernel (k_rescore_topk, one warp per row) recomputes the 8K scores of the kept groups from the
 //     same bf16 operands in fp32, re-applies the mask exactly and emits the sorted top-K (ties by item id).
 //
 //   warp 0      TMA producer (user tile resident, item K-blocks [256 x 64] bf16 through an mbarrier ring)
 //   warp 1      MMA issuer: tcgen05.mma.kind::f16 M128 N256 K16 into double-buffered fp32 TMEM accumulators,
-//               the tile's mask steps, then the real K steps
-//   warp 2      TMEM alloc / dealloc
-//   warp 3      mask builder: scatters the tile's pre-bucketed train entries (k_mask_buckets) into a ring of two
-//               32-slot mask buffers
+//               the tile's mask steps, then the real K steps; the next tile's barriers are checked behind three queued
+//               MMAs of the current one
+//   warp 2      TMEM alloc / dealloc; mask builder of the odd tiles (mask buffer 1)
+//   warp 3      mask builder of the even tiles (mask buffer 0): scatters the tile's pre-bucketed train entries into
+//               its 32-slot buffer
 //   warps 4-11  epilogue: one thread = one user row x one 128-column half of the tile
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -449,7 +453,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   const uint32_t bar_a = bar_empty + 8 * GQ_MAX_STAGES;
   const uint32_t bar_tfull = bar_a + 8;                           // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
-  // mask buffers: the 64-slot mask operand is a ring of two 32-slot buffers (K steps {0,1} and {2,3})
+  // mask buffers: the 64-slot mask operand is two 32-slot buffers (K steps {0,1} and {2,3}); tile `it` uses buffer it & 1
   const uint32_t bar_mfull = bar_tempty + 16;                     // [b] the builder published buffer b
   const uint32_t bar_mfree = bar_mfull + 16;                      // [b] the MMAs that read buffer b retired
   constexpr uint32_t kBarBytes = 8 * (2 * GQ_MAX_STAGES + 9);
@@ -459,7 +463,7 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   float* thr_all = reinterpret_cast<float*>(gbase + off_bar + kBarBytes + kMiscBytes);     // [EPI]
   float4* quart_all = reinterpret_cast<float4*>(gbase + off_bar + kBarBytes + kMiscBytes + 4 * GQ_EPI);   // [EPI], 16-byte aligned
 
-  // Roles: warps 0-7 epilogue, warp 8 TMA, warp 9 MMA, warp 10 TMEM alloc, warp 11 mask builder.  The single-lane
+  // Roles: warps 0-7 epilogue, warp 8 TMA, warp 9 MMA, warp 10 TMEM alloc + mask builder, warp 11 mask builder.  The single-lane
   // helper roles get the HIGHEST warp ids: the issue arbiter prefers higher warp ids, and the helpers (one per SM
   // sub-partition, each sharing it with two epilogue warps) are the serial resources of the pipeline.
   const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

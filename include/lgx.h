@@ -187,7 +187,11 @@ int lgx_pack_operand(const float* src, const int64_t* row_ids, int32_t rows, int
  * torch.topk at :135; the [B, M] score matrix never reaches HBM).
  *   U_op / I_op : fp32 [B,d] / [M,d] for LGX_SCORE_FP32 (U_op already gathered to the batch),
  *                 packed bf16 operands (lgx_pack_operand) for the tcgen05 modes;
- *   users       : int64[B] global user ids of the batch rows (mask lookup); may be NULL with g == NULL;
+ *   users       : int64[B] global user ids of the batch rows (mask lookup), or NULL = the identity batch (row u is
+ *                 user u, e.g. "all users in order").  For the identity batch the tcgen05 modes keep the graph's
+ *                 train mask in (user tile, item tile) buckets with the graph handle -- built by the first call,
+ *                 reused by the following ones, like the reference's dataset builds allPos once
+ *                 (PT/dataloader.py); LGX_SCORE_MASK_CACHE=0 buckets on every call as for explicit batches;
  *   g           : graph whose user rows hold the train items to exclude, or NULL for no mask;
  *   item_offset : global id of local item 0 (item-sharded catalogue); indices returned are global;
  *   out_idx/out_val : int64 / fp32 [B, k], sorted by score descending, ties by ascending item id.
