@@ -38,10 +38,10 @@ inline ScorePlan plan_score(int B, int M, int tile_users, int tile_items, int sm
 // Wave-aware variant for the tcgen05 kernel, whose CTAs share every row's running bound through global memory
 // (TcParams::row_bound): a split no longer restarts the threshold from scratch, so splits are cheap enough to be
 // used for making units / SMs nearly integral.  Cost model (tile units): waves(R) * (item_tiles / R + c0), with
-// c0 = the measured per-unit overhead (A tile reload, pipeline fill, list staging, the unit's early inserts)
-// ~ 14 item tiles: on B200 the Amazon-Book pass (412 user tiles x 358 item tiles) takes 2.15 / 2.29 / 2.32 / 2.41 /
-// 2.74 ms with R = 1 / 4 / 5 / 6 / 10, so it stays unsplit; a 4096-user batch x 250 K items (32 user tiles) went
-// from 5 splits = 160 units = 2 waves at 54 % (0.74 ms) to R = 9 = 1.95 waves (0.50 ms).
+// c0 = the measured per-unit overhead (A tile reload, pipeline fill, list staging, the unit's early inserts while
+// its thresholds are cold) in item tiles, passed in by the caller: 14 for the round-1 kernel; 60 for the group-queue
+// kernel, whose tiles cost half as much while a unit's start-up does not (lgx_score_gq.cu, kGqUnitOverheadTiles;
+// profiles/r2_score_split_sweep.txt).  The Amazon-Book pass (412 user tiles x 358 item tiles) stays unsplit either way.
 inline ScorePlan plan_score_waves(int B, int M, int tile_users, int tile_items, int sms, double unit_overhead_tiles) {
   ScorePlan p;
   p.n_user_tiles = (B + tile_users - 1) / tile_users;

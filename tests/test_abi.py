@@ -132,12 +132,16 @@ def test_score_plan_is_wave_aware(lib):
     # full Amazon-Book pass on 148 SMs: 412 user tiles = 2.78 waves; measured on B200: splitting loses -> 1 split
     p = _lgx.score_plan(52643, 91599, 64, 20, bf16, sms=148)
     assert (p["user_tiles"], p["item_tiles"], p["splits"]) == (412, 358, 1)
-    # 4096 users x 250 K items (BASELINE configs[4], one rank's shard): 32 user tiles; 9 splits = 288 units = 1.95 waves
+    # 4096 users x 250 K items (BASELINE configs[4], one rank's shard): 32 user tiles; 4 splits = 128 units = one wave
+    # (measured on B200 with the round-2 kernel: 0.286 ms; the 9 splits = 1.95 waves of the earlier fit: 0.323 ms)
     p = _lgx.score_plan(4096, 250000, 64, 20, bf16, sms=148)
-    assert p["user_tiles"] == 32 and p["splits"] == 9
-    # one rank of 8 on Amazon-Book: 52 user tiles; 5 splits = 260 units = 1.76 waves (the old rule gave 156 = 1.05)
+    assert p["user_tiles"] == 32 and p["splits"] == 4
+    # one rank of 8 on Amazon-Book: 52 user tiles; 2 splits = 104 units = one wave (0.263 ms; 5 splits: 0.293 ms)
     p = _lgx.score_plan(6581, 91599, 64, 20, bf16, sms=148)
-    assert p["user_tiles"] == 52 and p["splits"] == 5
+    assert p["user_tiles"] == 52 and p["splits"] == 2
+    # one rank of 4: 103 user tiles fit one wave unsplit (0.381 ms; 4 splits: 0.460 ms)
+    p = _lgx.score_plan(13161, 91599, 64, 20, bf16, sms=148)
+    assert p["user_tiles"] == 103 and p["splits"] == 1
     rng = np.random.default_rng(0)
     for _ in range(200):
         B, M = int(rng.integers(1, 200000)), int(rng.integers(20, 3000000))
