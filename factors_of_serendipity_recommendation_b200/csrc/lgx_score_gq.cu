@@ -476,7 +476,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
   // and otherwise ask the L2 for the same B tile at the same moment, tile after tile.  The list-walking mask
   // fallback needs ascending tiles, so a user tile without pre-bucketed entries keeps the plain order.
   int rot = 0;
-  if (p.rotate && n_my > 1 && !(p.has_mask && (p.mk_region == nullptr || p.mk_region[min(u_tile, (p.B - 1) / GQ_TILE_U)] < 0)))
+  // (the CTAs of a multicast cluster share every B tile and therefore one order: no rotation there)
+  if (p.rotate && !(p.cl > 1 && !(p.dbg & 128)) && n_my > 1 && !(p.has_mask && (p.mk_region == nullptr || p.mk_region[min(u_tile, (p.B - 1) / GQ_TILE_U)] < 0)))
     rot = (int)(((long long)u_tile * 40503LL) % n_my);
   auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_my ? t - n_my : t); };
   // Cluster mode (p.cl = 2 or 4 CTAs along x: neighbouring user tiles, the same item tiles): CTA r loads rows
@@ -1499,7 +1500,8 @@ int score_topk_gq(const lgx_graph* g, const void* U_op, const int64_t* users, in
     const size_t off_ent = off_ptr + ((sizeof(int32_t) * (size_t)plan.n_user_tiles * (n_tiles + 1) + 255) & ~(size_t)255);
     const size_t total = off_ent + sizeof(uint16_t) * cap + 256;
     // identity batch (users == NULL): the buckets depend on the graph only and are kept with it
-    static const bool cache_on = [] { const char* e = std::getenv("LGX_SCORE_MASK_CACHE"); return !e || std::atoi(e) != 0; }();
+    const char* ecache = std::getenv("LGX_SCORE_MASK_CACHE");          // re-read per call, like the other switches
+    const bool cache_on = !ecache || std::atoi(ecache) != 0;
     const bool cacheable = cache_on && users == nullptr;
     bool cached = false;
     unsigned char* base = nullptr;

@@ -112,6 +112,35 @@ def test_synthetic_shapes_and_ragged_tiles(d, mode, tol):
     check_topk(reference_raw_scores(ref, users[:5]), idx1.cpu().numpy(), val1.cpu().numpy(), 7, tol)
 
 
+@pytest.mark.parametrize("env", [{"LGX_SCORE_CLUSTER": "2"}, {"LGX_SCORE_CLUSTER": "4"}, {"LGX_SCORE_ROTATE": "1"},
+                                 {"LGX_SCORE_CLUSTER": "2", "LGX_SCORE_ROTATE": "1"}, {"LGX_SCORE_MASK_CACHE": "0"}])
+def test_optional_scoring_paths(env, monkeypatch):
+    """The opt-in paths of the tcgen05 kernel keep the contract: B-tile multicast across 2- and 4-CTA clusters (5 user
+    tiles: one / three padding CTAs that only load and release), the per-CTA rotated walk over the item tiles, and the
+    identity batch with and without the mask buckets kept in the graph handle.  All switches are read per call."""
+    from factors_of_serendipity_recommendation_b200 import _lgx, synth
+    nu, mi, d = 4 * 128 + 40, 7 * 256 + 19, 64
+    u, i = synth.make_interactions(nu, mi, 30000, seed=11)
+    ue, ie = synth.make_embeddings(nu, mi, d, seed=11, trained_like=True)
+    m, ds = make_model(nu, mi, u, i, 2, ue.numpy(), ie.numpy(), d=d)
+    ref = O.OracleLightGCN(nu, mi, u, i, latent_dim=d, n_layers=2, user_emb=ue, item_emb=ie)
+    users = np.arange(nu)
+    want = reference_raw_scores(ref, users)
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    for mode, tol in (("bf16", 1e-2), ("bf16x3", 1e-5)):
+        idx, val = m.topk(torch.from_numpy(users).cuda(), 20, mode=mode)
+        check_topk(want, idx.cpu().numpy(), val.cpu().numpy(), 20, tol)
+        # the identity batch straight through the C ABI (users = NULL), twice: built, then reused
+        with torch.no_grad():
+            au, ai = m.computer()
+        mid = _lgx.MODES[mode]
+        Uo, Io = _lgx.pack_operand(au, None, mid, False), _lgx.pack_operand(ai, None, mid, True)
+        for _ in range(2):
+            idx2, val2 = _lgx.score_topk(ds.getGraphHandle(), Uo, None, Io, d, 20, mid)
+            check_topk(want, idx2.cpu().numpy(), val2.cpu().numpy(), 20, tol)
+
+
 def test_no_mask_ties_and_fill():
     from factors_of_serendipity_recommendation_b200 import _lgx
     # exact ties: identical item rows -> lower item id first
