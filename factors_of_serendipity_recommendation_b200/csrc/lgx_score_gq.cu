@@ -79,8 +79,11 @@ constexpr int GQ_TMEM_BUF = 256;
 #ifndef LGX_GQ_LOW
 #define LGX_GQ_LOW 4
 #endif
-constexpr int GQ_GROUP = LGX_GQ_GROUP;          // columns per candidate group (4 or 8): 4 halves the rescoring work for
-                                                // twice the (cheap, predicated) appends of an epilogue that mostly waits
+// columns per candidate group: 8.  (4 halves the rescoring work -- 63 us less under ncu -- for twice the predicated
+// appends in the epilogue: measured 22 us slower per call before the bounded drains and 31 % slower with them; the
+// 4-column code paths are kept for A/B builds with -DLGX_GQ_GROUP=4.)
+constexpr int GQ_GROUP = LGX_GQ_GROUP;
+static_assert(GQ_GROUP == 8 || GQ_GROUP == 4, "groups of 4 or 8 columns");
 constexpr int GQ_SMEM_LIMIT = 232448;
 constexpr uint32_t GQ_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GQ_TILE_I >> 3) << 17) |
                               ((uint32_t)(GQ_TILE_U >> 4) << 24);
@@ -1005,7 +1008,8 @@ k_score_topk_gq(const __grid_constant__ CUtensorMap tmap_u, const __grid_constan
       // flush checks: a lane appends at most APC = 32 / GQ_GROUP candidates per chunk; small queues are checked with
       // a margin of 8 appends (every 2 chunks at 8-column groups), deep ones once per tile with a margin of 16
       constexpr int APC = 32 / GQ_GROUP;
-      constexpr int EVERY = SMALLQ ? LGX_GQ_EVERY : 4;   // chunks between two checks
+      // chunks between two checks; an 8-row queue must survive the appends in between (margin <= 8)
+      constexpr int EVERY = SMALLQ ? (LGX_GQ_EVERY * APC <= 8 ? LGX_GQ_EVERY : 8 / APC) : 4;
       constexpr int MARGIN = EVERY * APC;
       static_assert(!LGX_GQ_EARLY_CHUNK || EVERY >= 2, "two chunks are processed before the first check");
       auto check = [&](int chunks_done) {
